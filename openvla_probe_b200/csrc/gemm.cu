@@ -1,0 +1,112 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding and launch dispatch.
+#include "gemm.cuh"
+#include "host_util.h"
+
+namespace ovla {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, cols] tensor with `ld` elements between rows; box = [box_rows, 128 bytes]
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15))
+    return set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+template <int BN, int CG, int MODE, int KIND>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s, const GemmEpi& e,
+                      int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, CG, MODE, KIND>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tile_m = kBM * CG;
+  const int tiles = ((s.M + tile_m - 1) / tile_m) * ((s.N + BN - 1) / BN);
+  int workers = num_sms / CG;
+  if (workers > tiles) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, s, e));
+  count_launch();
+  return 0;
+}
+
+template <int MODE, int KIND>
+static int dispatch_tile(int bn, int cg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
+                         const GemmEpi& e, int num_sms, cudaStream_t stream) {
+  if (bn == 256 && cg == 2) return launch_one<256, 2, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+  if (bn == 256 && cg == 1) return launch_one<256, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+  if (bn == 128 && cg == 2) return launch_one<128, 2, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+  if (bn == 128 && cg == 1) return launch_one<128, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+  if (bn == 64 && cg == 1) return launch_one<64, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+  return set_error("gemm: unsupported tile config bn=%d cg=%d", bn, cg);
+}
+
+// Public (library-internal) entry. A: [M,K] lda; W: [N,K] ldw. kind: 0 bf16, 1 tf32(fp32 storage).
+int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
+                const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm: empty shape M=%d N=%d K=%d", M, N, K);
+  const int eb = kind == kKindBf16 ? 2 : 4;
+  if (mode == kModeBf16 && (N % 8)) return set_error("gemm: N=%d must be a multiple of 8", N);
+  if (mode == kModeSwiGLU && (N % 64)) return set_error("gemm: SwiGLU N=%d must be a multiple of 64", N);
+  if (mode == kModeF32 && (N % 4)) return set_error("gemm: N=%d must be a multiple of 4", N);
+  if (bn <= 0) {  // heuristic: biggest tile that still gives every SM work
+    const long long t256 = ((M + 255LL) / 256) * ((N + 255LL) / 256);
+    if (t256 * 2 >= num_sms) { bn = 256; cg = 2; }
+    else if (((M + 127LL) / 128) * ((N + 127LL) / 128) >= num_sms) { bn = 128; cg = 1; }
+    else { bn = 64; cg = 1; }
+  }
+  if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, A, eb, M, K, lda, kBM)) return -1;
+  if (make_tmap_2d(&tb, W, eb, N, K, ldw, bn / cg)) return -1;
+  GemmShape s{M, N, K};
+  if (kind == kKindBf16) {
+    if (mode == kModeBf16) return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
+    if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
+    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
+  } else {
+    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindTf32>(bn, cg, ta, tb, s, epi, num_sms, stream);
+  }
+  return set_error("gemm: unsupported mode=%d kind=%d", mode, kind);
+}
+
+}  // namespace ovla

@@ -1,0 +1,334 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
+//
+//   A  : activations, row-major (K contiguous)            -> TMA tile [BM x 128 B], SWIZZLE_128B
+//   W  : nn.Linear weight layout [N, K] (K contiguous)    -> TMA tile [BN x 128 B], SWIZZLE_128B
+//   acc: fp32 in TMEM, two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (tcgen05.ld -> registers -> fused math -> 16-byte global stores).
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2; each CTA stages its own 128 rows of A and half of the W tile, which halves the
+// shared-memory / L2 traffic per flop.
+//
+// Fused epilogues reproduce the rounding points of the reference's bf16 HF/timm forward (every torch op
+// output is rounded to bf16): linear(+bias) -> round -> [GELU -> round] -> [LayerScale -> round] ->
+// [residual add -> round];  SwiGLU: silu(round(g)) -> round -> * round(u) -> round.
+#pragma once
+#include "ptx.cuh"
+
+namespace ovla {
+
+enum GemmMode : int {
+  kModeBf16 = 0,    // bf16 out; optional bias / GELU / LayerScale / residual
+  kModeSwiGLU = 1,  // W rows interleaved [32 gate | 32 up]; out[M, N/2] = silu(g) * u
+  kModeF32 = 2,     // fp32 out; optional fp32-or-bf16 bias; optional rounding of the value to bf16
+};
+enum GemmKind : int { kKindBf16 = 0, kKindTf32 = 1 };
+
+struct GemmEpi {
+  void* out;
+  long long ldo;  // elements
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* scale;
+  const __nv_bfloat16* resid;
+  long long ldr;
+  const float* bias_f32;
+  int gelu;
+  int round_bf16;
+};
+
+struct GemmShape {
+  int M, N, K;  // N = rows of W (pre-epilogue output columns); K in elements
+};
+
+static constexpr int kGemmThreads = 256;
+static constexpr int kBM = 128;           // rows per CTA
+static constexpr int kStageABytes = kBM * 128;
+
+template <int BN, int CG>
+struct GemmCfg {
+  static constexpr int kBRows = BN / CG;                 // W rows staged per CTA
+  static constexpr int kStageBBytes = kBRows * 128;
+  static constexpr int kStageBytes = kStageABytes + kStageBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;               // 256 or 512 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int& mb, int& nb) {
+  constexpr int G = 8;
+  const int per_group = G * num_n;
+  const int g = t / per_group;
+  const int first_m = g * G;
+  const int gsz = min(G, num_m - first_m);
+  const int in_g = t - g * per_group;
+  mb = first_m + in_g % gsz;
+  nb = in_g / gsz;
+}
+
+template <int BN, int CG, int MODE, int KIND>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmShape shape, const GemmEpi epi) {
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kKElems = (KIND == kKindBf16) ? 64 : 32;  // elements per 128-byte K block
+  constexpr int kTileM = kBM * CG;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
+  const bool leader = (cta_rank == 0);
+
+  const int num_m = (shape.M + kTileM - 1) / kTileM;
+  const int num_n = (shape.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (shape.K + kKElems - 1) / kKElems;
+  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        int mb, nb;
+        gemm_tile_coords(t, num_m, num_n, mb, nb);
+        const int row_a = mb * kTileM + static_cast<int>(cta_rank) * kBM;
+        const int row_b = nb * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a);
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b);
+          } else {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a);
+            tma_load_2d_pair(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(KIND == kKindBf16 ? 1 : 2, kTileM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + kStageABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 MMAs of 32 bytes of K each per 128-byte block
+            if constexpr (KIND == kKindBf16)
+              umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else
+              umma_tf32<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 1) umma_commit(&tmem_full[acc]); else umma_commit_pair(&tmem_full[acc], 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < num_tiles; t += num_workers) {
+      int mb, nb;
+      gemm_tile_coords(t, num_m, num_n, mb, nb);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
+      const bool row_ok = row < shape.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const int col0 = nb * BN;
+
+      if constexpr (MODE == kModeBf16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
+        const __nv_bfloat16* res = epi.resid ? epi.resid + static_cast<long long>(row) * epi.ldr : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col = col0 + c * 32;
+          if (col >= shape.N) continue;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte store
+            const int cg = col + g * 8;
+            if (cg >= shape.N) break;
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+            if (epi.bias) {
+              const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
+              const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16(bw[i]);
+                x[2 * i] += f.x;
+                x[2 * i + 1] += f.y;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = bf16_round(x[i]);
+            if (epi.gelu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = bf16_round(gelu_erf(x[i]));
+            }
+            if (epi.scale) {
+              const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
+              const uint32_t sw[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16(sw[i]);
+                x[2 * i] = bf16_round(x[2 * i] * f.x);
+                x[2 * i + 1] = bf16_round(x[2 * i + 1] * f.y);
+              }
+            }
+            if (row_ok) {
+              if (res) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res + cg);
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(rw[i]);
+                  x[2 * i] += f.x;
+                  x[2 * i + 1] += f.y;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16(x[0], x[1]);
+              o.y = pack_bf16(x[2], x[3]);
+              o.z = pack_bf16(x[4], x[5]);
+              o.w = pack_bf16(x[6], x[7]);
+              *reinterpret_cast<uint4*>(out + cg) = o;
+            }
+          }
+        }
+      } else if constexpr (MODE == kModeSwiGLU) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
+        const int n_out = shape.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(taddr + c * 64, g);
+          tmem_ld32(taddr + c * 64 + 32, u);
+          tmem_ld_wait();
+          const int col = (col0 + c * 64) / 2;
+          if (col >= n_out) continue;
+#pragma unroll
+          for (int grp = 0; grp < 4; ++grp) {
+            const int cg = col + grp * 8;
+            if (cg >= n_out) break;
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]));
+              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]));
+              y[i] = bf16_round(silu(gv)) * uv;
+            }
+            if (row_ok) {
+              uint4 o;
+              o.x = pack_bf16(y[0], y[1]);
+              o.y = pack_bf16(y[2], y[3]);
+              o.z = pack_bf16(y[4], y[5]);
+              o.w = pack_bf16(y[6], y[7]);
+              *reinterpret_cast<uint4*>(out + cg) = o;
+            }
+          }
+        }
+      } else {  // kModeF32
+        float* out = reinterpret_cast<float*>(epi.out) + static_cast<long long>(row) * epi.ldo;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col = col0 + c * 32;
+          if (col >= shape.N) continue;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {  // 4 columns -> one 16-byte store
+            const int cg = col + g * 4;
+            if (cg >= shape.N) break;
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x[i] = __uint_as_float(v[g * 4 + i]);
+              if (epi.bias_f32) x[i] += epi.bias_f32[cg + i];
+              if (epi.bias) x[i] += __bfloat162float(epi.bias[cg + i]);
+              if (epi.round_bf16) x[i] = bf16_round(x[i]);
+            }
+            if (row_ok) *reinterpret_cast<float4*>(out + cg) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+        }
+      }
+
+      // release this accumulator buffer to the MMA issuer (of the leader CTA)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ------------------------------------------------------------ teardown
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace ovla
