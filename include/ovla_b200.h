@@ -52,6 +52,93 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
               int kind, void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, int tile_n, int cta_group,
               void* stream);
 
+
+/* LayerNorm(eps, affine) over rows of a bf16 [rows, D] matrix (timm Block.norm1/norm2). */
+int ovla_layernorm(const void* x_dev, long long ldx, const void* w_dev, const void* b_dev, float eps, void* out_dev,
+                   long long ldo, int rows, int D, void* stream);
+/* LlamaRMSNorm.forward (transformers modeling_llama.py): w * bf16(x * rsqrt(mean(x^2) + eps)). */
+int ovla_rmsnorm(const void* x_dev, long long ldx, const void* w_dev, float eps, void* out_dev, long long ldo,
+                 int rows, int D, void* stream);
+/* softmax(QK^T/sqrt(d))V. strides12 = element strides (batch, token, head) of Q, K, V, O in that order.
+ * head_dim 64 / 72 (timm Attention via SDPA) or 128 (Llama, causal=1). */
+int ovla_flash_attention(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev,
+                         const long long* strides12, int B, int H, int Tq, int Tk, int head_dim, int causal,
+                         void* stream);
+/* one-query attention over a KV cache [B, H, Tmax, 128] (cached generation, modeling_prismatic.py:325-341) */
+int ovla_decode_attention(const void* q_dev, long long q_ld, const void* k_cache_dev, const void* v_cache_dev, int B,
+                          int H, int head_dim, int Tmax, int ctx, void* out_dev, long long o_ld, void* stream);
+/* in-place RoPE on q of a fused [B*T, 3*H*hd] qkv buffer + rotated-k / v write into the KV cache at pos0+t */
+int ovla_rope_kv(void* qkv_dev, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
+                 void* k_cache_dev, void* v_cache_dev, int Tmax, void* stream);
+/* pool_tokens (experiments/robot/openvla_utils.py:126-137) for a whole batch: x bf16 [B, *, D] -> out fp32 [B, D].
+ * mode 0 = mean over rows [0, n_rows), 1 = "final" (row n_rows-1). */
+int ovla_pool_tokens(const void* x_dev, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                     float* out_dev, long long out_batch_stride, void* stream);
+/* torch.argmax(logits, -1) per row: first index of the maximum, NaN is maximal (greedy step of generate). */
+int ovla_argmax(const float* logits_dev, long long ld, int rows, int n, long long* out_dev, void* stream);
+/* de-tokenise + un-normalise (modeling_prismatic.py:521-534), float64, bit-identical to numpy. */
+int ovla_detokenize(const long long* ids_dev, int n, int action_dim, int vocab_size, const double* centers_dev,
+                    int n_centers, const double* q01_dev, const double* q99_dev, const unsigned char* mask_dev,
+                    double* out_dev, void* stream);
+/* small-batch (M <= 8) weight-streaming GEMM with the same epilogues as ovla_gemm */
+int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
+              void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream);
+
+/* ------------------------------------------------------------------ engine
+ * Stands behind OpenVLAForActionPrediction (modeling_prismatic.py:491-562) + get_vla_action's capture
+ * (experiments/robot/openvla_utils.py:186-203).  One fused pass: vision towers -> projector -> splice ->
+ * Llama prefill (KV cache + per-layer pooled hidden states) -> greedy cached decode.                       */
+typedef struct OvlaTower {
+  int dim, depth, heads, mlp, n_prefix, layerscale;
+} OvlaTower;
+
+typedef struct OvlaDims {
+  int image_size, patch;
+  int n_towers;        /* 2 = fused DINOv2+SigLIP (prism-dinosiglip-224px), 1 = single backbone */
+  OvlaTower towers[2];
+  int llm_dim, llm_inter, llm_layers, llm_heads, vocab;
+  float rms_eps;
+  int max_batch;       /* workspace is sized for this many observations per call */
+  int max_seq;         /* n_patches + prompt tokens + generated tokens, upper bound (KV capacity) */
+} OvlaDims;
+
+typedef struct OvlaEngine OvlaEngine;
+
+int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out);
+void ovla_destroy(OvlaEngine* e);
+/* Copy one bf16 tensor of the HF state_dict (names fixed by vla-scripts/extern/convert_openvla_weights_to_hf.py:73-115,
+ * e.g. "projector.fc1.weight", "language_model.model.layers.3.mlp.up_proj.weight") from device memory into the
+ * engine's packed layout (q/k/v stacked, gate/up interleaved, patch-embed K padded).  Extra names:
+ * "rope.cos" / "rope.sin" = bf16 [max_seq, head_dim/2] tables (LlamaRotaryEmbedding, cast to bf16).       */
+int ovla_bind_weight(OvlaEngine* e, const char* name, const void* src_dev, const long long* shape, int ndim);
+/* verifies that every tensor the path needs has been bound */
+int ovla_finalize(OvlaEngine* e);
+long long ovla_workspace_bytes(const OvlaEngine* e);
+long long ovla_weight_bytes(const OvlaEngine* e);
+
+typedef struct OvlaRunArgs {
+  const long long* input_ids_dev; /* int64 [B, P], first id = BOS; the host has already appended 29871 */
+  const void* pixel_values_dev;   /* bf16 [B, 3*n_towers, S, S]                                         */
+  int B, P;
+  int pool_len;        /* capture pools hidden-state rows [0, pool_len); 0 = no capture               */
+  int pool_mode;       /* 0 mean, 1 final                                                              */
+  int n_new_tokens;    /* greedy tokens to generate (action_dim); 0 = prefill only                     */
+  float* pooled_out_dev;          /* fp32 [llm_layers+1, B, llm_dim] or NULL                            */
+  long long* tokens_out_dev;      /* int64 [B, n_new_tokens] or NULL                                    */
+  float* step_logits_out_dev;     /* fp32 [n_new_tokens, B, vocab] or NULL (last-position logits)       */
+  void* hidden_out_dev;           /* bf16 [llm_layers+1, B, T, llm_dim] or NULL (forward(output_hidden_states)) */
+  void* projector_out_dev;        /* bf16 [B, n_patches, llm_dim] or NULL                               */
+  void* patches_out_dev;          /* bf16 [B, n_patches, vision_dim] or NULL (vision backbone output)   */
+} OvlaRunArgs;
+
+/* device-resident inputs/outputs */
+int ovla_run(OvlaEngine* e, const OvlaRunArgs* args, void* stream);
+/* Same, with HOST buffers (pinned or pageable): copies inputs H2D, runs, copies pooled/tokens back D2H and
+ * synchronises the stream.  This is the call the reference-facing predict_action makes.               */
+int ovla_run_host(OvlaEngine* e, const long long* input_ids_host, const void* pixel_values_host, int B, int P,
+                  int pool_len, int pool_mode, int n_new_tokens, float* pooled_out_host, long long* tokens_out_host,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

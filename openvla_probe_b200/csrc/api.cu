@@ -18,6 +18,23 @@ int ovla::num_sms() {
   return g_num_sms;
 }
 
+static GemmEpi to_epi(void* out, long long ldo, const OvlaGemmEpilogue* epi) {
+  GemmEpi e = {};
+  e.out = out;
+  e.ldo = ldo;
+  if (epi) {
+    e.bias = static_cast<const __nv_bfloat16*>(epi->bias_bf16);
+    e.scale = static_cast<const __nv_bfloat16*>(epi->scale_bf16);
+    e.resid = static_cast<const __nv_bfloat16*>(epi->resid_bf16);
+    e.ldr = epi->ld_resid;
+    e.bias_f32 = epi->bias_f32;
+    e.gelu = epi->gelu;
+    e.round_bf16 = epi->round_bf16;
+  }
+  return e;
+}
+
+
 extern "C" {
 
 int ovla_abi_version(void) { return OVLA_ABI_VERSION; }
@@ -42,6 +59,46 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
   }
   return gemm_launch(a_dev, lda, w_dev, ldw, M, N, K, mode, kind, e, tile_n, cta_group, num_sms(),
                      static_cast<cudaStream_t>(stream));
+}
+
+
+int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
+              void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream) {
+  return gemv_launch(x_dev, ldx, w_dev, ldw, M, N, K, mode, to_epi(out_dev, ldo, epi), static_cast<cudaStream_t>(stream));
+}
+int ovla_layernorm(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
+                   int rows, int D, void* stream) {
+  return layernorm_launch(x, ldx, w, b, eps, out, ldo, rows, D, static_cast<cudaStream_t>(stream));
+}
+int ovla_rmsnorm(const void* x, long long ldx, const void* w, float eps, void* out, long long ldo, int rows, int D,
+                 void* stream) {
+  return rmsnorm_launch(x, ldx, w, eps, out, ldo, rows, D, static_cast<cudaStream_t>(stream));
+}
+int ovla_flash_attention(const void* q, const void* k, const void* v, void* o, const long long* strides12, int B, int H,
+                         int Tq, int Tk, int head_dim, int causal, void* stream) {
+  if (!strides12) return set_error("ovla_flash_attention: null strides");
+  return flash_attn_launch(q, k, v, o, strides12, B, H, Tq, Tk, head_dim, causal, static_cast<cudaStream_t>(stream));
+}
+int ovla_decode_attention(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
+                          int Tmax, int ctx, void* out, long long o_ld, void* stream) {
+  return decode_attn_launch(q, q_ld, kc, vc, B, H, head_dim, Tmax, ctx, out, o_ld, static_cast<cudaStream_t>(stream));
+}
+int ovla_rope_kv(void* qkv, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
+                 void* kc, void* vc, int Tmax, void* stream) {
+  return rope_kv_launch(qkv, B, T, H, head_dim, pos0, cos_dev, sin_dev, kc, vc, Tmax, static_cast<cudaStream_t>(stream));
+}
+int ovla_pool_tokens(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                     float* out, long long out_batch_stride, void* stream) {
+  return pool_tokens_launch(x, batch_stride, ld, B, n_rows, D, mode, out, out_batch_stride,
+                            static_cast<cudaStream_t>(stream));
+}
+int ovla_argmax(const float* logits, long long ld, int rows, int n, long long* out, void* stream) {
+  return argmax_launch(logits, ld, rows, n, out, static_cast<cudaStream_t>(stream));
+}
+int ovla_detokenize(const long long* ids, int n, int action_dim, int vocab_size, const double* centers, int n_centers,
+                    const double* q01, const double* q99, const unsigned char* mask, double* out, void* stream) {
+  return detok_unnorm_launch(ids, n, action_dim, vocab_size, centers, n_centers, q01, q99, mask, out,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

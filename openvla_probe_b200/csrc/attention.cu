@@ -1,0 +1,376 @@
+// Attention kernels.
+//  * flash_attn_kernel: tiled online-softmax attention for the 256/261-token bidirectional ViT blocks (head_dim 64
+//    and 72) and the causal Llama prefill (head_dim 128).  One CTA = 64 query rows of one (batch, head); K/V tiles
+//    of 64 keys are double-buffered in shared memory with cp.async; S = QK^T and O += PV run on the warp-level
+//    tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate).  Attention is < 1 % of the path's flops
+//    (21.8 of 4157 GFLOP per action), so this kernel is sized for correctness and low traffic; the
+//    tcgen05 budget goes to the GEMMs that carry 99 % of the work.
+//  * decode_attn_kernel: single-query attention over the KV cache for the 6 cached decode steps -- pure
+//    HBM streaming of K and V ([ctx, 128] bf16 each per (batch, head)), 16-byte coalesced loads.
+// Softmax is computed in fp32 and probabilities are rounded to bf16 before the PV product, as flash-attn does.
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace ovla {
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = smem_u32(dst);
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero-fill the 16 bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnStrides {
+  long long q_b, q_t, q_h;  // element strides of Q[b][t][h][:]
+  long long k_b, k_t, k_h;
+  long long v_b, v_t, v_h;
+  long long o_b, o_t, o_h;
+};
+
+// HD: real head dim; HDP: head dim padded to a multiple of 16 (zero-filled in smem)
+template <int HD, int HDP, bool CAUSAL>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q,
+                                                         const __nv_bfloat16* __restrict__ K,
+                                                         const __nv_bfloat16* __restrict__ V,
+                                                         __nv_bfloat16* __restrict__ O, AttnStrides st, int Tq, int Tk,
+                                                         float scale_log2) {
+  constexpr int LD = HDP + 8;           // padded smem row (elements): conflict-free ldmatrix
+  constexpr int CH = HDP / 8;           // 16-byte chunks per row
+  constexpr int KS = HDP / 16;          // k-steps of QK^T
+  constexpr int NT = HDP / 8;           // n-tiles of the output
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);  // [64][LD]
+  __nv_bfloat16* sK = sQ + 64 * LD;                                  // [2][64][LD]
+  __nv_bfloat16* sV = sK + 2 * 64 * LD;                              // [2][64][LD]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* Qb = Q + b * st.q_b + h * st.q_h;
+  const __nv_bfloat16* Kb = K + b * st.k_b + h * st.k_h;
+  const __nv_bfloat16* Vb = V + b * st.v_b + h * st.v_h;
+
+  auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, long long tstride, int t0, int tmax) {
+    for (int i = tid; i < 64 * CH; i += 128) {
+      const int r = i / CH, c = (i % CH) * 8;
+      const bool ok = (t0 + r < tmax) && (c < HD);
+      const __nv_bfloat16* g = src + static_cast<long long>(ok ? t0 + r : 0) * tstride + (ok ? c : 0);
+      cp_async16(dst + r * LD + c, g, ok);
+    }
+  };
+
+  int n_kt = (Tk + 63) / 64;
+  if (CAUSAL) {
+    const int last_q = min(q0 + 63, Tq - 1);
+    n_kt = min(n_kt, last_q / 64 + 1);
+  }
+  load_tile(sQ, Qb, st.q_t, q0, Tq);
+  load_tile(sK, Kb, st.k_t, 0, Tk);
+  load_tile(sV, Vb, st.v_t, 0, Tk);
+  cp_async_commit();
+
+  uint32_t qf[KS][4];
+  float o_acc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, tq = lane & 3;
+  const int qrow0 = q0 + warp * 16 + g;  // this thread's two query rows: qrow0, qrow0 + 8
+
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_kt) {
+      load_tile(sK + (buf ^ 1) * 64 * LD, Kb, st.k_t, (kt + 1) * 64, Tk);
+      load_tile(sV + (buf ^ 1) * 64 * LD, Vb, st.v_t, (kt + 1) * 64, Tk);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kt == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int c = ks * 16 + 8 * (lane >> 4);
+        ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + r * LD + c);
+      }
+    }
+    const __nv_bfloat16* k_s = sK + buf * 64 * LD;
+    const __nv_bfloat16* v_s = sV + buf * 64 * LD;
+
+    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // two key n-tiles per ldmatrix.x4
+        uint32_t b0, b1, b2, b3;
+        const int r = np * 16 + (lane & 7) + 8 * (lane >> 4);
+        const int c = ks * 16 + 8 * ((lane >> 3) & 1);
+        ldsm_x4(b0, b1, b2, b3, k_s + r * LD + c);
+        mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+      }
+    }
+    // ---- mask + online softmax (rows qrow0 and qrow0+8; this thread holds cols n*8 + 2*tq + {0,1})
+    const int key0 = kt * 64;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = key0 + n * 8 + 2 * tq + (j & 1);
+        const int qr = qrow0 + 8 * (j >> 1);
+        const bool ok = key < Tk && (!CAUSAL || key <= qr);
+        s[n][j] = ok ? s[n][j] * scale_log2 : -INFINITY;
+        mx[j >> 1] = fmaxf(mx[j >> 1], s[n][j]);
+      }
+    }
+    float corr[2], m_new[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      m_new[r] = fmaxf(m_run[r], mx[r]);
+      const float m_use = (m_new[r] == -INFINITY) ? 0.f : m_new[r];
+      corr[r] = exp2f(m_run[r] - m_use);  // m_run = -inf -> 0
+      m_run[r] = m_new[r];
+      m_new[r] = m_use;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = exp2f(s[n][0] - m_new[0]), p1 = exp2f(s[n][1] - m_new[0]);
+      const float p2 = exp2f(s[n][2] - m_new[1]), p3 = exp2f(s[n][3] - m_new[1]);
+      const uint32_t lo = pack_bf16(p0, p1), hi = pack_bf16(p2, p3);
+      const float2 l2 = unpack_bf16(lo), h2 = unpack_bf16(hi);  // row sums use the rounded probabilities
+      rs[0] += l2.x + l2.y;
+      rs[1] += h2.x + h2.y;
+      pf[n >> 1][(n & 1) * 2 + 0] = lo;
+      pf[n >> 1][(n & 1) * 2 + 1] = hi;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      o_acc[n][0] *= corr[0];
+      o_acc[n][1] *= corr[0];
+      o_acc[n][2] *= corr[1];
+      o_acc[n][3] *= corr[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int r = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int c = np * 16 + 8 * (lane >> 4);
+        ldsm_x4_t(b0, b1, b2, b3, v_s + r * LD + c);
+        mma_bf16_16816(o_acc[2 * np], pf[kk], b0, b1);
+        mma_bf16_16816(o_acc[2 * np + 1], pf[kk], b2, b3);
+      }
+    }
+    __syncthreads();  // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+
+  // ---- normalise and write (stage the warp's 16 x HD tile through its own rows of sQ for 16-byte stores)
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    inv[r] = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+  }
+  __nv_bfloat16* sO = sQ + warp * 16 * LD;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    *reinterpret_cast<uint32_t*>(sO + g * LD + n * 8 + 2 * tq) = pack_bf16(o_acc[n][0] * inv[0], o_acc[n][1] * inv[0]);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LD + n * 8 + 2 * tq) =
+        pack_bf16(o_acc[n][2] * inv[1], o_acc[n][3] * inv[1]);
+  }
+  __syncwarp();
+  __nv_bfloat16* Ob = O + b * st.o_b + h * st.o_h;
+  constexpr int OCH = HD / 8;
+  for (int i = lane; i < 16 * OCH; i += 32) {
+    const int r = i / OCH, c = (i % OCH) * 8;
+    const int t = q0 + warp * 16 + r;
+    if (t < Tq) *reinterpret_cast<uint4*>(Ob + t * st.o_t + c) = *reinterpret_cast<const uint4*>(sO + r * LD + c);
+  }
+}
+
+template <int HD, int HDP, bool CAUSAL>
+static int flash_launch_t(const void* Q, const void* K, const void* V, void* O, const AttnStrides& s, int B, int H,
+                          int Tq, int Tk, cudaStream_t st) {
+  constexpr int LD = HDP + 8;
+  constexpr int smem = 5 * 64 * LD * 2;
+  auto kern = flash_attn_kernel<HD, HDP, CAUSAL>;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  dim3 grid((Tq + 63) / 64, H, B);
+  kern<<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K),
+                               static_cast<const __nv_bfloat16*>(V), static_cast<__nv_bfloat16*>(O), s, Tq, Tk,
+                               scale_log2);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Q/K/V/O element strides (batch, token, head); head vectors contiguous and 16-byte aligned.
+int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
+                      int Tq, int Tk, int head_dim, int causal, cudaStream_t st) {
+  if (B <= 0 || H <= 0 || Tq <= 0) return 0;
+  if (Tk <= 0) return set_error("attention: empty key range");
+  AttnStrides s;
+  s.q_b = strides12[0]; s.q_t = strides12[1]; s.q_h = strides12[2];
+  s.k_b = strides12[3]; s.k_t = strides12[4]; s.k_h = strides12[5];
+  s.v_b = strides12[6]; s.v_t = strides12[7]; s.v_h = strides12[8];
+  s.o_b = strides12[9]; s.o_t = strides12[10]; s.o_h = strides12[11];
+  for (int i = 0; i < 12; ++i)
+    if (strides12[i] % 8) return set_error("attention: strides must be multiples of 8 elements (16 bytes)");
+  if (head_dim == 64 && !causal) return flash_launch_t<64, 64, false>(Q, K, V, O, s, B, H, Tq, Tk, st);
+  if (head_dim == 72 && !causal) return flash_launch_t<72, 80, false>(Q, K, V, O, s, B, H, Tq, Tk, st);
+  if (head_dim == 128 && causal) return flash_launch_t<128, 128, true>(Q, K, V, O, s, B, H, Tq, Tk, st);
+  if (head_dim == 128 && !causal) return flash_launch_t<128, 128, false>(Q, K, V, O, s, B, H, Tq, Tk, st);
+  if (head_dim == 64 && causal) return flash_launch_t<64, 64, true>(Q, K, V, O, s, B, H, Tq, Tk, st);
+  return set_error("attention: unsupported head_dim=%d causal=%d", head_dim, causal);
+}
+
+// ------------------------------------------------------------------------------------------- decode attention
+// q [B, H, HD] (row stride q_ld per batch), cache K/V [B, H, Tmax, HD]; ctx keys valid; out [B, H*HD].
+// CTA per (h, b), 128 threads.  Phase 1: half-warp per key, 16-byte loads, shuffle-reduced dot products.
+// Phase 2: softmax over smem scores.  Phase 3: thread d accumulates sum_j p_j V[j][d] (coalesced rows).
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld,
+                                                          const __nv_bfloat16* __restrict__ kc,
+                                                          const __nv_bfloat16* __restrict__ vc, int Tmax, int ctx,
+                                                          __nv_bfloat16* __restrict__ out, long long o_ld,
+                                                          float scale) {
+  static_assert(HD == 128, "decode attention is specialised for head_dim 128");
+  extern __shared__ float sc[];  // [ctx]
+  __shared__ float red[4];
+  const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hl = lane & 15, half = lane >> 4;
+  const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * H + h) * Tmax * HD;
+  const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * H + h) * Tmax * HD;
+  float qv[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(q + b * q_ld + h * HD + hl * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(w[i]);
+      qv[2 * i] = f.x;
+      qv[2 * i + 1] = f.y;
+    }
+  }
+  for (int j0 = warp * 2; j0 < ctx; j0 += 8) {
+    const int j = j0 + half;
+    float d = 0.f;
+    if (j < ctx) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * HD + hl * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        d += f.x * qv[2 * i] + f.y * qv[2 * i + 1];
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (hl == 0 && j < ctx) sc[j] = d * scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < ctx; j += 128) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < ctx; j += 128) {
+    const float p = __expf(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  // phase 3: 16 lanes x 8 dims cover a 256-byte V row; 8 row-groups (128 threads / 16) stride over keys
+  const int grp = tid >> 4;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int j = grp; j < ctx; j += 8) {
+    const float p = bf16_round(sc[j] * inv);
+    const uint4 u = *reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * HD + hl * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(w[i]);
+      acc[2 * i] += p * f.x;
+      acc[2 * i + 1] += p * f.y;
+    }
+  }
+  __syncthreads();  // scores no longer needed: reuse smem for the cross-group reduction
+  float* ra = sc;   // needs 8 * 128 floats (host guarantees the allocation)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ra[grp * HD + hl * 8 + i] = acc[i];
+  __syncthreads();
+  float o = 0.f;
+#pragma unroll
+  for (int gI = 0; gI < 8; ++gI) o += ra[gI * HD + tid];
+  out[b * o_ld + h * HD + tid] = __float2bfloat16_rn(o);
+}
+
+int decode_attn_launch(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
+                       int Tmax, int ctx, void* out, long long o_ld, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (head_dim != 128) return set_error("decode attention: head_dim %d unsupported (128 only)", head_dim);
+  if (ctx <= 0 || ctx > Tmax) return set_error("decode attention: ctx=%d out of range (Tmax=%d)", ctx, Tmax);
+  const int smem = (ctx > 8 * 128 ? ctx : 8 * 128) * sizeof(float);
+  if (smem > 48 * 1024) return set_error("decode attention: ctx=%d too long", ctx);
+  dim3 grid(H, B);
+  decode_attn_kernel<128><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(q), q_ld,
+                                                   static_cast<const __nv_bfloat16*>(kc),
+                                                   static_cast<const __nv_bfloat16*>(vc), Tmax, ctx,
+                                                   static_cast<__nv_bfloat16*>(out), o_ld,
+                                                   1.0f / sqrtf(static_cast<float>(head_dim)));
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace ovla

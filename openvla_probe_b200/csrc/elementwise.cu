@@ -1,0 +1,377 @@
+// HBM-bound data-movement kernels of the predict_action path: patch im2col, ViT token assembly, tower concat,
+// embedding gather + multimodal splice, RoPE + KV-cache write, hidden-state pooling (capture), argmax,
+// de-tokenise / un-normalise.  All use 16-byte accesses along the contiguous dimension.
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace ovla {
+
+// ------------------------------------------------------------------------------------------- im2col
+// pixel_values [B, C_total, H, W] bf16 -> patches [B*np, Kpad], K index = (c, kh, kw) as Conv2d weight.flatten(1)
+// (timm PatchEmbed: Conv2d(3, D, 14, 14) reached through modeling_prismatic.py:121). Columns >= 3*p*p are zero.
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ px, int c_total, int c0, int H, int Wd, int patch,
+                              int Kpad, __nv_bfloat16* __restrict__ out, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx % Kpad);
+  const long long row = idx / Kpad;
+  const int gw = Wd / patch, gh = H / patch;
+  const int np = gw * gh;
+  const int b = static_cast<int>(row / np), p = static_cast<int>(row % np);
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (k < 3 * patch * patch) {
+    const int c = k / (patch * patch), r = k % (patch * patch);
+    const int kh = r / patch, kw = r % patch;
+    const int y = (p / gw) * patch + kh, x = (p % gw) * patch + kw;
+    v = px[((static_cast<long long>(b) * c_total + c0 + c) * H + y) * Wd + x];
+  }
+  out[idx] = v;
+}
+
+int im2col_launch(const void* px, int B, int c_total, int c0, int H, int W, int patch, int Kpad, void* out,
+                  cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * Kpad;
+  if (total <= 0) return 0;
+  im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(px), c_total, c0, H, W, patch, Kpad, static_cast<__nv_bfloat16*>(out), total);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- ViT token assembly
+// tokens[b, n_prefix + p, :] = bf16(patch[b, p, :] + pos[p, :]);  tokens[b, 0] = cls; tokens[b, 1..] = reg
+// (timm VisionTransformer._pos_embed with no_embed_class=True: pos-embed is added to the patches only.)
+__global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const __nv_bfloat16* __restrict__ pos,
+                                       const __nv_bfloat16* __restrict__ cls, const __nv_bfloat16* __restrict__ reg,
+                                       int np, int n_prefix, int D, __nv_bfloat16* __restrict__ tokens,
+                                       long long total_vec) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int dv = D / 8;
+  const int c = static_cast<int>(idx % dv) * 8;
+  const long long row = idx / dv;
+  const int N = np + n_prefix;
+  const int b = static_cast<int>(row / N), t = static_cast<int>(row % N);
+  uint4 o;
+  if (t == 0 && n_prefix) {
+    o = *reinterpret_cast<const uint4*>(cls + c);
+  } else if (t < n_prefix) {
+    o = *reinterpret_cast<const uint4*>(reg + static_cast<long long>(t - 1) * D + c);
+  } else {
+    const int p = t - n_prefix;
+    const uint4 a = *reinterpret_cast<const uint4*>(patch + (static_cast<long long>(b) * np + p) * D + c);
+    const uint4 e = *reinterpret_cast<const uint4*>(pos + static_cast<long long>(p) * D + c);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, eu[4] = {e.x, e.y, e.z, e.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16(au[i]), y = unpack_bf16(eu[i]);
+      r[i] = pack_bf16(x.x + y.x, x.y + y.y);
+    }
+    o = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+  *reinterpret_cast<uint4*>(tokens + row * D + c) = o;
+}
+
+int assemble_tokens_launch(const void* patch, const void* pos, const void* cls, const void* reg, int B, int np,
+                           int n_prefix, int D, void* tokens, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (np + n_prefix) * (D / 8);
+  if (total <= 0) return 0;
+  assemble_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(patch), static_cast<const __nv_bfloat16*>(pos),
+      static_cast<const __nv_bfloat16*>(cls), static_cast<const __nv_bfloat16*>(reg), np, n_prefix, D,
+      static_cast<__nv_bfloat16*>(tokens), total);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- strided 2-D copy
+// dst[b, r, dcol0 + c] = src[b, srow0 + r, c]  (prefix strip + channel concat, modeling_prismatic.py:123)
+__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, long long src_batch, long long src_ld,
+                                 int srow0, __nv_bfloat16* __restrict__ dst, long long dst_batch, long long dst_ld,
+                                 int dcol0, int rows, int cols, long long total_vec) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = cols / 8;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const long long rr = idx / cv;
+  const int b = static_cast<int>(rr / rows), r = static_cast<int>(rr % rows);
+  *reinterpret_cast<uint4*>(dst + b * dst_batch + r * dst_ld + dcol0 + c) =
+      *reinterpret_cast<const uint4*>(src + b * src_batch + (srow0 + r) * src_ld + c);
+}
+
+int copy_rows_launch(const void* src, long long src_batch, long long src_ld, int srow0, void* dst, long long dst_batch,
+                     long long dst_ld, int dcol0, int B, int rows, int cols, cudaStream_t st) {
+  if (cols % 8 || dcol0 % 8) return set_error("copy_rows: cols/dcol0 must be multiples of 8");
+  const long long total = static_cast<long long>(B) * rows * (cols / 8);
+  if (total <= 0) return 0;
+  copy_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(src), src_batch, src_ld, srow0, static_cast<__nv_bfloat16*>(dst), dst_batch,
+      dst_ld, dcol0, rows, cols, total);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- embed + splice
+// x[b, 0] = E[ids[b,0]];  x[b, 1..np] = proj[b, :];  x[b, np+j] = E[ids[b,j]], j >= 1
+// (modeling_prismatic.py:380-385: [BOS | projected patches | text[1:]])
+__global__ void embed_splice_kernel(const long long* __restrict__ ids, int P, const __nv_bfloat16* __restrict__ E,
+                                    int vocab, const __nv_bfloat16* __restrict__ proj, int np, int D,
+                                    __nv_bfloat16* __restrict__ x, long long total_vec, int* __restrict__ err) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int dv = D / 8;
+  const int c = static_cast<int>(idx % dv) * 8;
+  const long long row = idx / dv;
+  const int T = np + P;
+  const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+  const __nv_bfloat16* src;
+  if (t >= 1 && t <= np) {
+    src = proj + (static_cast<long long>(b) * np + (t - 1)) * D;
+  } else {
+    const int j = (t == 0) ? 0 : t - np;
+    long long id = ids[static_cast<long long>(b) * P + j];
+    if (id < 0 || id >= vocab) {
+      if (c == 0) atomicExch(err, 1);
+      id = 0;
+    }
+    src = E + id * D;
+  }
+  *reinterpret_cast<uint4*>(x + row * D + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+int embed_splice_launch(const void* ids, int B, int P, const void* E, int vocab, const void* proj, int np, int D,
+                        void* x, int* err_flag, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (np + P) * (D / 8);
+  if (total <= 0) return 0;
+  embed_splice_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const long long*>(ids), P, static_cast<const __nv_bfloat16*>(E), vocab,
+      static_cast<const __nv_bfloat16*>(proj), np, D, static_cast<__nv_bfloat16*>(x), total, err_flag);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- RoPE + KV write
+// qkv [B*T, 3*D] (q | k | v, each [H, hd]) -> q rotated in place; k rotated and v copied into the layer's
+// KV cache [B, H, Tmax, hd] at position pos0 + t.  cos/sin tables [Tmax, hd/2] are bf16 (HF casts the fp32
+// cos/sin to the activation dtype), and  q*cos + rotate_half(q)*sin  rounds every product and the sum to bf16
+// exactly like the reference's elementwise bf16 ops (transformers modeling_llama.py apply_rotary_pos_emb).
+__global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int T, int H, int hd, int pos0,
+                               const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int Tmax,
+                               long long total) {
+  // one thread per (row, head, 8-element group of the first half)
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int half = hd / 2, gv = half / 8;
+  const int g = static_cast<int>(idx % gv) * 8;
+  long long r = idx / gv;
+  const int h = static_cast<int>(r % H);
+  r /= H;  // row = b*T + t
+  const int t = static_cast<int>(r % T), b = static_cast<int>(r / T);
+  const int pos = pos0 + t;
+  const int D = H * hd;
+  const uint4 cu = *reinterpret_cast<const uint4*>(cos_t + static_cast<long long>(pos) * half + g);
+  const uint4 su = *reinterpret_cast<const uint4*>(sin_t + static_cast<long long>(pos) * half + g);
+  const uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+  __nv_bfloat16* base = qkv + r * 3 * D + h * hd;
+  const long long cache_off = ((static_cast<long long>(b) * H + h) * Tmax + pos) * hd;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {  // 0: q, 1: k
+    __nv_bfloat16* p = base + which * D;
+    const uint4 lo = *reinterpret_cast<const uint4*>(p + g);
+    const uint4 hi = *reinterpret_cast<const uint4*>(p + half + g);
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x1 = unpack_bf16(lw[i]), x2 = unpack_bf16(hw[i]);
+      const float2 c = unpack_bf16(cw[i]), s = unpack_bf16(sw[i]);
+      // first half:  x1*cos + (-x2)*sin ; second half: x2*cos + x1*sin   (cos/sin identical for both halves)
+      ol[i] = pack_bf16(bf16_round(x1.x * c.x) + bf16_round(-x2.x * s.x), bf16_round(x1.y * c.y) + bf16_round(-x2.y * s.y));
+      oh[i] = pack_bf16(bf16_round(x2.x * c.x) + bf16_round(x1.x * s.x), bf16_round(x2.y * c.y) + bf16_round(x1.y * s.y));
+    }
+    const uint4 vlo = make_uint4(ol[0], ol[1], ol[2], ol[3]), vhi = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    if (which == 0) {
+      *reinterpret_cast<uint4*>(p + g) = vlo;
+      *reinterpret_cast<uint4*>(p + half + g) = vhi;
+    } else {
+      *reinterpret_cast<uint4*>(kc + cache_off + g) = vlo;
+      *reinterpret_cast<uint4*>(kc + cache_off + half + g) = vhi;
+    }
+  }
+  const __nv_bfloat16* pv = base + 2 * D;
+  *reinterpret_cast<uint4*>(vc + cache_off + g) = *reinterpret_cast<const uint4*>(pv + g);
+  *reinterpret_cast<uint4*>(vc + cache_off + half + g) = *reinterpret_cast<const uint4*>(pv + half + g);
+}
+
+int rope_kv_launch(void* qkv, int B, int T, int H, int hd, int pos0, const void* cos_t, const void* sin_t, void* kc,
+                   void* vc, int Tmax, cudaStream_t st) {
+  if (hd % 16) return set_error("rope: head_dim %d must be a multiple of 16", hd);
+  if (pos0 + T > Tmax) return set_error("rope: position %d exceeds KV capacity %d", pos0 + T, Tmax);
+  const long long total = static_cast<long long>(B) * T * H * (hd / 16);
+  if (total <= 0) return 0;
+  rope_kv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<__nv_bfloat16*>(qkv), T, H, hd, pos0, static_cast<const __nv_bfloat16*>(cos_t),
+      static_cast<const __nv_bfloat16*>(sin_t), static_cast<__nv_bfloat16*>(kc), static_cast<__nv_bfloat16*>(vc),
+      Tmax, total);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- capture pooling
+// experiments/robot/openvla_utils.py:126-131,193-199:  hs.float().mean(1)  or  hs[:, -1]  per layer.
+// x [B, T(ld rows), D] bf16 -> out [B, D] fp32.  mode 0: mean over rows [0, n_rows); mode 1: row n_rows-1.
+// CTA = 8 warps over 256 columns; warp w sums rows w, w+8, ... with 16-byte loads; smem tree over warps.
+__global__ void __launch_bounds__(256) pool_tokens_kernel(const __nv_bfloat16* __restrict__ x, long long batch_stride,
+                                                          long long ld, int n_rows, int D, int mode,
+                                                          float* __restrict__ out, long long out_batch_stride) {
+  __shared__ float red[8][256];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* xb = x + b * batch_stride;
+  if (col < D) {
+    if (mode == 1) {
+      if (warp == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(n_rows - 1) * ld + col);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(u[i]);
+          acc[2 * i] = f.x;
+          acc[2 * i + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int r = warp; r < n_rows; r += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(r) * ld + col);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(u[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    out[b * out_batch_stride + c] = (mode == 0) ? s / static_cast<float>(n_rows) : s;
+  }
+}
+
+int pool_tokens_launch(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                       float* out, long long out_batch_stride, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (n_rows <= 0) return set_error("pool_tokens: empty token range");
+  if (D % 8) return set_error("pool_tokens: D must be a multiple of 8");
+  dim3 grid((D + 255) / 256, B);
+  pool_tokens_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), batch_stride, ld, n_rows, D, mode,
+                                          out, out_batch_stride);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- argmax
+// torch.argmax semantics on fp32 rows: first index of the maximum; NaN counts as the maximum.
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn != bn) return vn;
+  if (vn) return i < bi;
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, long long ld, int n,
+                                                          long long* __restrict__ out) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* row = x + blockIdx.x * ld;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  const int nv = n / 4;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * i);
+    const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (better(a[j], 4 * i + j, bv, bi)) { bv = a[j]; bi = 4 * i + j; }
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n; i += 256)
+    if (better(row[i], i, bv, bi)) { bv = row[i]; bi = i; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+    out[blockIdx.x] = bi;
+  }
+}
+
+int argmax_launch(const float* x, long long ld, int rows, int n, long long* out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (n <= 0) return set_error("argmax: empty rows");
+  if (ld % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return set_error("argmax: rows must be 16-byte aligned");
+  argmax_rows_kernel<<<rows, 256, 0, st>>>(x, ld, n, out);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- de-tokenise
+// modeling_prismatic.py:521-534: disc = clip(vocab - id - 1, 0, n_centers-1); norm = centers[disc];
+// action = mask ? 0.5*(norm+1)*(q99-q01)+q01 : norm -- float64, evaluated with explicit round-to-nearest
+// mul/add (no FMA contraction) so the result is bit-identical to numpy.
+__global__ void detok_unnorm_kernel(const long long* __restrict__ ids, int n, int action_dim, int vocab_size,
+                                    const double* __restrict__ centers, int n_centers, const double* __restrict__ q01,
+                                    const double* __restrict__ q99, const unsigned char* __restrict__ mask,
+                                    double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = i % action_dim;
+  long long disc = static_cast<long long>(vocab_size) - ids[i] - 1;
+  disc = disc < 0 ? 0 : (disc > n_centers - 1 ? n_centers - 1 : disc);
+  const double c = centers[disc];
+  double r = c;
+  if (mask[a]) {
+    const double t0 = __dmul_rn(0.5, __dadd_rn(c, 1.0));
+    const double t1 = __dmul_rn(t0, __dadd_rn(q99[a], -q01[a]));
+    r = __dadd_rn(t1, q01[a]);
+  }
+  out[i] = r;
+}
+
+int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_size, const double* centers,
+                        int n_centers, const double* q01, const double* q99, const unsigned char* mask, double* out,
+                        cudaStream_t st) {
+  if (n <= 0) return 0;
+  detok_unnorm_kernel<<<(n + 127) / 128, 128, 0, st>>>(ids, n, action_dim, vocab_size, centers, n_centers, q01, q99,
+                                                        mask, out);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace ovla

@@ -1,0 +1,616 @@
+// OvlaEngine: owns the packed bf16 weights and the HBM workspace of one GPU and runs the fused
+// predict_action + hidden-state-capture pass (see include/ovla_b200.h).
+//
+// HBM layout (all bf16 unless noted; B = observations per call, N_t = prefix + patches of tower t):
+//   weights   : per tower  patch_w [D, Kpad], pos [np, D], cls/reg, per block {ln1, qkv_w [3D, D], proj_w, ls1,
+//               ln2, fc1_w [mlp, D], fc2_w [D, mlp], ls2};  projector fc1..3;  LLM embed [V, D], per layer
+//               {ln1, qkv_w [3D, D] (q|k|v stacked), o_w, ln2, gate_up_w [2I, D] (32-row interleave), down_w [D, I]},
+//               final norm, lm_head [V, D];  RoPE cos/sin [max_seq, hd/2].
+//   workspace : ViT   im2col [B*np, Kpad] | patch [B*np, D] | x [B*N, D] | h [B*N, D] | qkv [B*N, 3D] |
+//                     attn [B*N, D] | mlp [B*N, mlp]       (sized for the wider tower, reused by both)
+//               proj  patches [B*np, Dv] | p1 [B*np, 4Dv] | p2 [B*np, D_llm] | p3 [B*np, D_llm]
+//               LLM   x [B*T, D] | h [B*T, D] | qkv [B*T, 3D] | attn [B*T, D] | act [B*T, I]
+//               KV    [layers][2][B, H, max_seq, hd]
+//               out   pooled fp32 [layers+1, B, D] | logits fp32 [B, V] | tokens int64 [n_new, B]
+#include <math.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ovla_b200.h"
+#include "host_util.h"
+#include "ops.h"
+
+using namespace ovla;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+struct Slot {
+  bf16* ptr = nullptr;
+  long long rows = 0, cols = 0;  // logical 2-D shape of the packed destination
+  bool bound = false;
+  bool required = true;
+};
+
+struct BlockW {
+  Slot ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ls1, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b, ls2;
+};
+struct TowerW {
+  Slot patch_w, patch_b, pos, cls, reg;
+  std::vector<BlockW> blocks;
+};
+struct LayerW {
+  Slot ln1, qkv_w, o_w, ln2, gate_up_w, down_w;
+  bool q_bound = false, k_bound = false, v_bound = false, gate_bound = false, up_bound = false;
+};
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct OvlaEngine {
+  OvlaDims d;
+  int device = 0;
+  int np = 0, kpad = 0, vision_dim = 0, head_dim = 0;
+  int n_run[2] = {0, 0};  // blocks actually executed per tower (depth - 1: the last block's output is never used)
+
+  // weights
+  std::vector<void*> allocs;
+  long long weight_bytes = 0, workspace_bytes = 0;
+  TowerW tower[2];
+  Slot pj_w[3], pj_b[3];
+  int n_proj = 0;
+  Slot embed, final_norm, lm_head, rope_cos, rope_sin;
+  std::vector<LayerW> layers;
+
+  // workspace
+  bf16 *v_im2col = nullptr, *v_patch = nullptr, *v_x = nullptr, *v_h = nullptr, *v_qkv = nullptr, *v_attn = nullptr,
+       *v_mlp = nullptr;
+  bf16 *p_cat = nullptr, *p_1 = nullptr, *p_2 = nullptr, *p_3 = nullptr;
+  bf16 *l_x = nullptr, *l_h = nullptr, *l_qkv = nullptr, *l_attn = nullptr, *l_act = nullptr;
+  bf16* kv = nullptr;
+  float *pooled = nullptr, *logits = nullptr;
+  long long* tokens = nullptr;
+  int* err_flag = nullptr;
+  // staging for ovla_run_host
+  long long* in_ids = nullptr;
+  bf16* in_px = nullptr;
+  long long* out_tokens = nullptr;
+  int max_P = 0;
+
+  template <typename T>
+  int alloc(T** p, long long n_elems, bool is_weight) {
+    void* q = nullptr;
+    const long long bytes = round_up(n_elems * static_cast<long long>(sizeof(T)), 256);
+    CUDA_TRY(cudaMalloc(&q, bytes));
+    allocs.push_back(q);
+    (is_weight ? weight_bytes : workspace_bytes) += bytes;
+    *p = static_cast<T*>(q);
+    return 0;
+  }
+  int alloc_slot(Slot& s, long long rows, long long cols, bool required = true) {
+    s.rows = rows;
+    s.cols = cols;
+    s.required = required;
+    return alloc(&s.ptr, rows * cols, true);
+  }
+  long long kv_layer_elems() const {
+    return 2LL * d.max_batch * d.llm_heads * d.max_seq * head_dim;
+  }
+  bf16* k_cache(int layer) const { return kv + layer * kv_layer_elems(); }
+  bf16* v_cache(int layer) const { return k_cache(layer) + kv_layer_elems() / 2; }
+};
+
+static int check_dims(const OvlaDims& d) {
+  if (d.n_towers < 1 || d.n_towers > 2) return set_error("n_towers must be 1 or 2");
+  if (d.image_size % d.patch) return set_error("image_size must be a multiple of patch");
+  for (int t = 0; t < d.n_towers; ++t) {
+    const OvlaTower& w = d.towers[t];
+    if (w.dim % w.heads) return set_error("tower %d: dim %% heads != 0", t);
+    const int hd = w.dim / w.heads;
+    if (hd != 64 && hd != 72 && hd != 128) return set_error("tower %d: head_dim %d unsupported (64/72/128)", t, hd);
+    if (w.dim % 8 || w.mlp % 8) return set_error("tower %d: dim/mlp must be multiples of 8", t);
+    if (w.depth < 2) return set_error("tower %d: depth must be >= 2", t);
+  }
+  if (d.llm_dim % d.llm_heads || d.llm_dim / d.llm_heads != 128) return set_error("LLM head_dim must be 128");
+  if (d.llm_inter % 32) return set_error("llm_inter must be a multiple of 32");
+  if (d.vocab % 8) return set_error("vocab must be a multiple of 8");
+  if (d.max_batch < 1 || d.max_seq < 2) return set_error("max_batch / max_seq too small");
+  return 0;
+}
+
+extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
+  if (!dims || !out) return set_error("ovla_create: null argument");
+  OVLA_TRY(check_dims(*dims));
+  CUDA_TRY(cudaSetDevice(device));
+  OvlaEngine* e = new OvlaEngine();
+  e->d = *dims;
+  e->device = device;
+  const OvlaDims& d = e->d;
+  const int g = d.image_size / d.patch;
+  e->np = g * g;
+  e->kpad = static_cast<int>(round_up(3 * d.patch * d.patch, 8));
+  e->head_dim = d.llm_dim / d.llm_heads;
+  e->vision_dim = 0;
+  int rc = 0;
+  auto A = [&](Slot& s, long long r, long long c, bool req = true) { if (!rc) rc = e->alloc_slot(s, r, c, req); };
+  for (int t = 0; t < d.n_towers && !rc; ++t) {
+    const OvlaTower& w = d.towers[t];
+    e->vision_dim += w.dim;
+    e->n_run[t] = w.depth - 1;
+    TowerW& tw = e->tower[t];
+    A(tw.patch_w, w.dim, e->kpad);
+    A(tw.patch_b, 1, w.dim);
+    A(tw.pos, e->np, w.dim);
+    if (w.n_prefix) {
+      A(tw.cls, 1, w.dim);
+      if (w.n_prefix > 1) A(tw.reg, w.n_prefix - 1, w.dim);
+    }
+    tw.blocks.resize(e->n_run[t]);
+    for (BlockW& b : tw.blocks) {
+      A(b.ln1_w, 1, w.dim); A(b.ln1_b, 1, w.dim);
+      A(b.qkv_w, 3LL * w.dim, w.dim); A(b.qkv_b, 1, 3LL * w.dim);
+      A(b.proj_w, w.dim, w.dim); A(b.proj_b, 1, w.dim);
+      A(b.ln2_w, 1, w.dim); A(b.ln2_b, 1, w.dim);
+      A(b.fc1_w, w.mlp, w.dim); A(b.fc1_b, 1, w.mlp);
+      A(b.fc2_w, w.dim, w.mlp); A(b.fc2_b, 1, w.dim);
+      if (w.layerscale) { A(b.ls1, 1, w.dim); A(b.ls2, 1, w.dim); }
+    }
+    if (!rc) rc = cudaMemset(tw.patch_w.ptr, 0, sizeof(bf16) * w.dim * e->kpad) == cudaSuccess ? 0 : set_error("memset");
+  }
+  const int Dv = e->vision_dim, Dl = d.llm_dim;
+  if (d.n_towers == 2) {  // fused-gelu-mlp (modeling_prismatic.py:139-144)
+    e->n_proj = 3;
+    A(e->pj_w[0], 4LL * Dv, Dv); A(e->pj_b[0], 1, 4LL * Dv);
+    A(e->pj_w[1], Dl, 4LL * Dv); A(e->pj_b[1], 1, Dl);
+    A(e->pj_w[2], Dl, Dl);       A(e->pj_b[2], 1, Dl);
+  } else {                // gelu-mlp (modeling_prismatic.py:135-137)
+    e->n_proj = 2;
+    A(e->pj_w[0], Dl, Dv); A(e->pj_b[0], 1, Dl);
+    A(e->pj_w[1], Dl, Dl); A(e->pj_b[1], 1, Dl);
+  }
+  A(e->embed, d.vocab, Dl);
+  e->layers.resize(d.llm_layers);
+  for (LayerW& l : e->layers) {
+    A(l.ln1, 1, Dl);
+    A(l.qkv_w, 3LL * Dl, Dl);
+    A(l.o_w, Dl, Dl);
+    A(l.ln2, 1, Dl);
+    A(l.gate_up_w, 2LL * d.llm_inter, Dl);
+    A(l.down_w, Dl, d.llm_inter);
+  }
+  A(e->final_norm, 1, Dl);
+  A(e->lm_head, d.vocab, Dl);
+  A(e->rope_cos, d.max_seq, e->head_dim / 2);
+  A(e->rope_sin, d.max_seq, e->head_dim / 2);
+
+  // ---- workspace
+  const long long B = d.max_batch;
+  long long maxN = 0, maxD = 0, maxMlp = 0;
+  for (int t = 0; t < d.n_towers; ++t) {
+    maxN = std::max<long long>(maxN, e->np + d.towers[t].n_prefix);
+    maxD = std::max<long long>(maxD, d.towers[t].dim);
+    maxMlp = std::max<long long>(maxMlp, d.towers[t].mlp);
+  }
+  auto W = [&](auto** p, long long n) { if (!rc) rc = e->alloc(p, n, false); };
+  W(&e->v_im2col, B * e->np * e->kpad);
+  W(&e->v_patch, B * e->np * maxD);
+  W(&e->v_x, B * maxN * maxD);
+  W(&e->v_h, B * maxN * maxD);
+  W(&e->v_qkv, B * maxN * 3 * maxD);
+  W(&e->v_attn, B * maxN * maxD);
+  W(&e->v_mlp, B * maxN * maxMlp);
+  W(&e->p_cat, B * e->np * Dv);
+  W(&e->p_1, B * e->np * std::max<long long>(4LL * Dv, Dl));
+  W(&e->p_2, B * e->np * Dl);
+  W(&e->p_3, B * e->np * Dl);
+  const long long T = d.max_seq;
+  W(&e->l_x, B * T * Dl);
+  W(&e->l_h, B * T * Dl);
+  W(&e->l_qkv, B * T * 3 * Dl);
+  W(&e->l_attn, B * T * Dl);
+  W(&e->l_act, B * T * d.llm_inter);
+  W(&e->kv, e->kv_layer_elems() * d.llm_layers);
+  W(&e->pooled, (d.llm_layers + 1LL) * B * Dl);
+  W(&e->logits, B * d.vocab);
+  W(&e->tokens, 64LL * B);
+  W(&e->err_flag, 4);
+  e->max_P = static_cast<int>(T - e->np);
+  W(&e->in_ids, B * std::max(1, e->max_P));
+  W(&e->in_px, B * 3LL * d.n_towers * d.image_size * d.image_size);
+  W(&e->out_tokens, 64LL * B);
+  if (!rc) rc = cudaMemset(e->err_flag, 0, 16) == cudaSuccess ? 0 : set_error("memset");
+  if (rc) {
+    std::string msg = last_error();
+    ovla_destroy(e);
+    set_error("ovla_create: %s", msg.c_str());
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" void ovla_destroy(OvlaEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+extern "C" long long ovla_workspace_bytes(const OvlaEngine* e) { return e ? e->workspace_bytes : 0; }
+extern "C" long long ovla_weight_bytes(const OvlaEngine* e) { return e ? e->weight_bytes : 0; }
+
+// ----------------------------------------------------------------------------------------------- weight binding
+static long long numel(const long long* shape, int ndim) {
+  long long n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  return n;
+}
+
+static int copy_plain(Slot& s, const void* src, const long long* shape, int ndim, const char* name) {
+  if (numel(shape, ndim) != s.rows * s.cols)
+    return set_error("bind %s: expected %lld elements, got %lld", name, s.rows * s.cols, numel(shape, ndim));
+  CUDA_TRY(cudaMemcpy(s.ptr, src, sizeof(bf16) * s.rows * s.cols, cudaMemcpyDeviceToDevice));
+  s.bound = true;
+  return 0;
+}
+
+static bool starts_with(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+static int bind_tower(OvlaEngine* e, int t, const std::string& rest, const void* src, const long long* shape, int ndim,
+                      const char* full) {
+  TowerW& tw = e->tower[t];
+  const OvlaTower& w = e->d.towers[t];
+  if (rest == "patch_embed.proj.weight") {
+    const long long k = 3LL * e->d.patch * e->d.patch;
+    if (numel(shape, ndim) != w.dim * k) return set_error("bind %s: bad shape", full);
+    CUDA_TRY(cudaMemcpy2D(tw.patch_w.ptr, sizeof(bf16) * e->kpad, src, sizeof(bf16) * k, sizeof(bf16) * k, w.dim,
+                          cudaMemcpyDeviceToDevice));
+    tw.patch_w.bound = true;
+    return 0;
+  }
+  if (rest == "patch_embed.proj.bias") return copy_plain(tw.patch_b, src, shape, ndim, full);
+  if (rest == "pos_embed") return copy_plain(tw.pos, src, shape, ndim, full);
+  if (rest == "cls_token" && w.n_prefix) return copy_plain(tw.cls, src, shape, ndim, full);
+  if (rest == "reg_token" && w.n_prefix > 1) return copy_plain(tw.reg, src, shape, ndim, full);
+  if (starts_with(rest, "blocks.")) {
+    const size_t dot = rest.find('.', 7);
+    if (dot == std::string::npos) return set_error("bind %s: malformed block name", full);
+    const int i = atoi(rest.substr(7, dot - 7).c_str());
+    if (i < 0 || i >= w.depth) return set_error("bind %s: block index out of range", full);
+    if (i >= e->n_run[t]) return 0;  // last block: executed by timm, output discarded (modeling_prismatic.py:85-87)
+    BlockW& b = tw.blocks[i];
+    const std::string leaf = rest.substr(dot + 1);
+    struct { const char* n; Slot* s; } tab[] = {
+        {"norm1.weight", &b.ln1_w}, {"norm1.bias", &b.ln1_b}, {"attn.qkv.weight", &b.qkv_w},
+        {"attn.qkv.bias", &b.qkv_b}, {"attn.proj.weight", &b.proj_w}, {"attn.proj.bias", &b.proj_b},
+        {"norm2.weight", &b.ln2_w}, {"norm2.bias", &b.ln2_b}, {"mlp.fc1.weight", &b.fc1_w},
+        {"mlp.fc1.bias", &b.fc1_b}, {"mlp.fc2.weight", &b.fc2_w}, {"mlp.fc2.bias", &b.fc2_b},
+        {"ls1.scale_factor", &b.ls1}, {"ls2.scale_factor", &b.ls2}};
+    for (auto& x : tab)
+      if (leaf == x.n) {
+        if (!x.s->ptr) return set_error("bind %s: tower has no LayerScale", full);
+        return copy_plain(*x.s, src, shape, ndim, full);
+      }
+  }
+  // attn_pool.*, norm.*, fc_norm.* exist in checkpoints but are never executed on this path
+  if (starts_with(rest, "attn_pool.") || starts_with(rest, "norm.") || starts_with(rest, "fc_norm.")) return 0;
+  return set_error("bind %s: unknown vision tensor", full);
+}
+
+extern "C" int ovla_bind_weight(OvlaEngine* e, const char* cname, const void* src, const long long* shape, int ndim) {
+  if (!e || !cname || !src || !shape) return set_error("ovla_bind_weight: null argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const std::string name(cname);
+  const OvlaDims& d = e->d;
+  if (starts_with(name, "vision_backbone.featurizer."))
+    return bind_tower(e, 0, name.substr(27), src, shape, ndim, cname);
+  if (starts_with(name, "vision_backbone.fused_featurizer.")) {
+    if (d.n_towers < 2) return set_error("bind %s: engine has a single tower", cname);
+    return bind_tower(e, 1, name.substr(33), src, shape, ndim, cname);
+  }
+  if (starts_with(name, "projector.fc")) {
+    const int i = name[12] - '1';
+    if (i < 0 || i >= e->n_proj) return set_error("bind %s: projector has %d layers", cname, e->n_proj);
+    if (name.substr(13) == ".weight") return copy_plain(e->pj_w[i], src, shape, ndim, cname);
+    if (name.substr(13) == ".bias") return copy_plain(e->pj_b[i], src, shape, ndim, cname);
+    return set_error("bind %s: unknown projector tensor", cname);
+  }
+  if (name == "rope.cos") return copy_plain(e->rope_cos, src, shape, ndim, cname);
+  if (name == "rope.sin") return copy_plain(e->rope_sin, src, shape, ndim, cname);
+  if (name == "language_model.model.embed_tokens.weight") return copy_plain(e->embed, src, shape, ndim, cname);
+  if (name == "language_model.model.norm.weight") return copy_plain(e->final_norm, src, shape, ndim, cname);
+  if (name == "language_model.lm_head.weight") return copy_plain(e->lm_head, src, shape, ndim, cname);
+  const char* lp = "language_model.model.layers.";
+  if (starts_with(name, lp)) {
+    const size_t p0 = strlen(lp), dot = name.find('.', p0);
+    if (dot == std::string::npos) return set_error("bind %s: malformed layer name", cname);
+    const int i = atoi(name.substr(p0, dot - p0).c_str());
+    if (i < 0 || i >= d.llm_layers) return set_error("bind %s: layer index out of range", cname);
+    LayerW& l = e->layers[i];
+    const std::string leaf = name.substr(dot + 1);
+    const long long Dl = d.llm_dim, I = d.llm_inter;
+    if (leaf == "input_layernorm.weight") return copy_plain(l.ln1, src, shape, ndim, cname);
+    if (leaf == "post_attention_layernorm.weight") return copy_plain(l.ln2, src, shape, ndim, cname);
+    if (leaf == "self_attn.o_proj.weight") return copy_plain(l.o_w, src, shape, ndim, cname);
+    if (leaf == "mlp.down_proj.weight") return copy_plain(l.down_w, src, shape, ndim, cname);
+    for (int j = 0; j < 3; ++j) {
+      const char* nm[3] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight"};
+      if (leaf == nm[j]) {
+        if (numel(shape, ndim) != Dl * Dl) return set_error("bind %s: bad shape", cname);
+        CUDA_TRY(cudaMemcpy(l.qkv_w.ptr + j * Dl * Dl, src, sizeof(bf16) * Dl * Dl, cudaMemcpyDeviceToDevice));
+        (j == 0 ? l.q_bound : j == 1 ? l.k_bound : l.v_bound) = true;
+        l.qkv_w.bound = l.q_bound && l.k_bound && l.v_bound;
+        return 0;
+      }
+    }
+    for (int j = 0; j < 2; ++j) {
+      const char* nm[2] = {"mlp.gate_proj.weight", "mlp.up_proj.weight"};
+      if (leaf == nm[j]) {  // rows [32b, 32b+32) of gate -> rows [64b, 64b+32); of up -> [64b+32, 64b+64)
+        if (numel(shape, ndim) != I * Dl) return set_error("bind %s: bad shape", cname);
+        const size_t blk = sizeof(bf16) * 32 * Dl;
+        CUDA_TRY(cudaMemcpy2D(l.gate_up_w.ptr + j * 32 * Dl, 2 * blk, src, blk, blk, I / 32, cudaMemcpyDeviceToDevice));
+        (j == 0 ? l.gate_bound : l.up_bound) = true;
+        l.gate_up_w.bound = l.gate_bound && l.up_bound;
+        return 0;
+      }
+    }
+    if (leaf == "self_attn.rotary_emb.inv_freq") return 0;
+  }
+  return set_error("bind %s: unknown tensor name", cname);
+}
+
+extern "C" int ovla_finalize(OvlaEngine* e) {
+  if (!e) return set_error("ovla_finalize: null engine");
+  std::string missing;
+  int n_missing = 0;
+  auto chk = [&](const Slot& s, const std::string& nm) {
+    if (s.ptr && s.required && !s.bound) {
+      if (n_missing < 6) missing += (missing.empty() ? "" : ", ") + nm;
+      ++n_missing;
+    }
+  };
+  for (int t = 0; t < e->d.n_towers; ++t) {
+    const std::string p = t == 0 ? "featurizer." : "fused_featurizer.";
+    TowerW& tw = e->tower[t];
+    chk(tw.patch_w, p + "patch_embed.proj.weight"); chk(tw.patch_b, p + "patch_embed.proj.bias");
+    chk(tw.pos, p + "pos_embed"); chk(tw.cls, p + "cls_token"); chk(tw.reg, p + "reg_token");
+    for (size_t i = 0; i < tw.blocks.size(); ++i) {
+      BlockW& b = tw.blocks[i];
+      const std::string q = p + "blocks." + std::to_string(i) + ".";
+      chk(b.ln1_w, q + "norm1.weight"); chk(b.ln1_b, q + "norm1.bias"); chk(b.qkv_w, q + "attn.qkv.weight");
+      chk(b.qkv_b, q + "attn.qkv.bias"); chk(b.proj_w, q + "attn.proj.weight"); chk(b.proj_b, q + "attn.proj.bias");
+      chk(b.ln2_w, q + "norm2.weight"); chk(b.ln2_b, q + "norm2.bias"); chk(b.fc1_w, q + "mlp.fc1.weight");
+      chk(b.fc1_b, q + "mlp.fc1.bias"); chk(b.fc2_w, q + "mlp.fc2.weight"); chk(b.fc2_b, q + "mlp.fc2.bias");
+      chk(b.ls1, q + "ls1.scale_factor"); chk(b.ls2, q + "ls2.scale_factor");
+    }
+  }
+  for (int i = 0; i < e->n_proj; ++i) {
+    chk(e->pj_w[i], "projector.fc" + std::to_string(i + 1) + ".weight");
+    chk(e->pj_b[i], "projector.fc" + std::to_string(i + 1) + ".bias");
+  }
+  chk(e->embed, "embed_tokens.weight"); chk(e->final_norm, "model.norm.weight"); chk(e->lm_head, "lm_head.weight");
+  chk(e->rope_cos, "rope.cos"); chk(e->rope_sin, "rope.sin");
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    LayerW& l = e->layers[i];
+    const std::string q = "layers." + std::to_string(i) + ".";
+    chk(l.ln1, q + "input_layernorm.weight"); chk(l.qkv_w, q + "self_attn.{q,k,v}_proj.weight");
+    chk(l.o_w, q + "self_attn.o_proj.weight"); chk(l.ln2, q + "post_attention_layernorm.weight");
+    chk(l.gate_up_w, q + "mlp.{gate,up}_proj.weight"); chk(l.down_w, q + "mlp.down_proj.weight");
+  }
+  if (n_missing) return set_error("ovla_finalize: %d tensors not bound (%s%s)", n_missing, missing.c_str(),
+                                  n_missing > 6 ? ", ..." : "");
+  CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------- forward
+namespace {
+
+// out = A . W^T with epilogue; picks the weight-streaming kernel for M <= 8
+int linear(const bf16* A, long long lda, const Slot& W, int M, int mode, void* out, long long ldo, const bf16* bias,
+           const bf16* scale, const bf16* resid, long long ldr, int gelu, int round_bf16, cudaStream_t st) {
+  GemmEpi epi = {};
+  epi.out = out;
+  epi.ldo = ldo;
+  epi.bias = bias;
+  epi.scale = scale;
+  epi.resid = resid;
+  epi.ldr = ldr;
+  epi.gelu = gelu;
+  epi.round_bf16 = round_bf16;
+  const int N = static_cast<int>(W.rows), K = static_cast<int>(W.cols);
+  if (M <= 8) return gemv_launch(A, lda, W.ptr, K, M, N, K, mode, epi, st);
+  return gemm_launch(A, lda, W.ptr, K, M, N, K, mode, kKindBf16, epi, 0, 0, num_sms(), st);
+}
+
+int run_tower(OvlaEngine* e, int t, const bf16* px, int B, cudaStream_t st) {
+  const OvlaDims& d = e->d;
+  const OvlaTower& w = d.towers[t];
+  TowerW& tw = e->tower[t];
+  const int np = e->np, N = np + w.n_prefix, D = w.dim, hd = D / w.heads;
+  const int rows = B * N;
+  // patch embed: im2col -> GEMM(+bias) -> (+pos_embed, prefix tokens)
+  OVLA_TRY(im2col_launch(px, B, 3 * d.n_towers, 3 * t, d.image_size, d.image_size, d.patch, e->kpad, e->v_im2col, st));
+  OVLA_TRY(linear(e->v_im2col, e->kpad, tw.patch_w, B * np, kModeBf16, e->v_patch, D, tw.patch_b.ptr, nullptr, nullptr,
+                  0, 0, 0, st));
+  OVLA_TRY(assemble_tokens_launch(e->v_patch, tw.pos.ptr, tw.cls.ptr, tw.reg.ptr, B, np, w.n_prefix, D, e->v_x, st));
+  const long long s12[12] = {3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd,
+                             1LL * D * N, D, hd};
+  for (int i = 0; i < e->n_run[t]; ++i) {
+    BlockW& b = tw.blocks[i];
+    OVLA_TRY(layernorm_launch(e->v_x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, e->v_h, D, rows, D, st));
+    OVLA_TRY(linear(e->v_h, D, b.qkv_w, rows, kModeBf16, e->v_qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(flash_attn_launch(e->v_qkv, e->v_qkv + D, e->v_qkv + 2 * D, e->v_attn, s12, B, w.heads, N, N, hd, 0, st));
+    // x = x + ls1(proj(attn))   (in place: each epilogue thread reads its residual before writing)
+    OVLA_TRY(linear(e->v_attn, D, b.proj_w, rows, kModeBf16, e->v_x, D, b.proj_b.ptr, b.ls1.ptr, e->v_x, D, 0, 0, st));
+    OVLA_TRY(layernorm_launch(e->v_x, D, b.ln2_w.ptr, b.ln2_b.ptr, 1e-6f, e->v_h, D, rows, D, st));
+    OVLA_TRY(linear(e->v_h, D, b.fc1_w, rows, kModeBf16, e->v_mlp, w.mlp, b.fc1_b.ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e->v_mlp, w.mlp, b.fc2_w, rows, kModeBf16, e->v_x, D, b.fc2_b.ptr, b.ls2.ptr, e->v_x, D, 0, 0, st));
+  }
+  // strip prefix tokens, concat on the feature dim (modeling_prismatic.py:123)
+  int col0 = 0;
+  for (int u = 0; u < t; ++u) col0 += d.towers[u].dim;
+  OVLA_TRY(copy_rows_launch(e->v_x, 1LL * N * D, D, w.n_prefix, e->p_cat, 1LL * np * e->vision_dim, e->vision_dim, col0,
+                            B, np, D, st));
+  return 0;
+}
+
+int run_llm_layers(OvlaEngine* e, int B, int T, int pos0, const OvlaRunArgs* a, bool prefill, cudaStream_t st) {
+  const OvlaDims& d = e->d;
+  const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim, rows = B * T;
+  const int Tmax = d.max_seq;
+  const long long s12[12] = {3LL * D * T, 3LL * D, hd,                                   // q in the fused buffer
+                             1LL * H * Tmax * hd, hd, 1LL * Tmax * hd,                   // k cache [B,H,Tmax,hd]
+                             1LL * H * Tmax * hd, hd, 1LL * Tmax * hd, 1LL * D * T, D, hd};
+  for (int i = 0; i < d.llm_layers; ++i) {
+    LayerW& l = e->layers[i];
+    if (prefill) {
+      if (a->pool_len > 0)
+        OVLA_TRY(pool_tokens_launch(e->l_x, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
+                                    e->pooled + 1LL * i * B * D, D, st));
+      if (a->hidden_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
+                                 sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
+    }
+    OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, rows, D, st));
+    OVLA_TRY(linear(e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
+    // NB: the KV cache batch stride is max_batch-independent: caches are indexed [b][h][t] with b < B
+    OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, pos0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i),
+                            e->v_cache(i), Tmax, st));
+    if (prefill) {
+      OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
+    } else {
+      OVLA_TRY(decode_attn_launch(e->l_qkv, 3LL * D, e->k_cache(i), e->v_cache(i), B, H, hd, Tmax, pos0 + 1,
+                                  e->l_attn, D, st));
+    }
+    OVLA_TRY(linear(e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));
+    OVLA_TRY(linear(e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,
+                    0, st));
+    OVLA_TRY(linear(e->l_act, d.llm_inter, l.down_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+  }
+  // final norm (hidden_states[L] is post-norm)
+  OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, rows, D, st));
+  if (prefill) {
+    if (a->pool_len > 0)
+      OVLA_TRY(pool_tokens_launch(e->l_h, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
+                                  e->pooled + 1LL * d.llm_layers * B * D, D, st));
+    if (a->hidden_out_dev)
+      CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * d.llm_layers * rows * D, e->l_h,
+                               sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
+  if (!e || !a) return set_error("ovla_run: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const OvlaDims& d = e->d;
+  const int B = a->B, P = a->P, np = e->np, D = d.llm_dim;
+  if (B == 0) return 0;  // empty batch: nothing to do
+  if (B < 0 || B > d.max_batch) return set_error("ovla_run: batch %d exceeds max_batch %d", B, d.max_batch);
+  if (P < 1) return set_error("ovla_run: prompt must hold at least the BOS token");
+  const int T = np + P;
+  const int n_new = a->n_new_tokens;
+  if (n_new < 0 || n_new > 64) return set_error("ovla_run: n_new_tokens out of range");
+  if (T + std::max(0, n_new - 1) > d.max_seq)
+    return set_error("ovla_run: sequence %d + %d new tokens exceeds max_seq %d", T, n_new, d.max_seq);
+  if (a->pool_len < 0 || a->pool_len > T) return set_error("ovla_run: pool_len %d out of range (T=%d)", a->pool_len, T);
+  if (!a->input_ids_dev || !a->pixel_values_dev) return set_error("ovla_run: null input");
+  // The KV cache is laid out for the live batch: [B, H, max_seq, hd] per layer half (capacity max_batch).
+
+  // ---- vision towers + projector
+  for (int t = 0; t < d.n_towers; ++t) OVLA_TRY(run_tower(e, t, static_cast<const bf16*>(a->pixel_values_dev), B, st));
+  const int Mp = B * np, Dv = e->vision_dim;
+  if (a->patches_out_dev)
+    CUDA_TRY(cudaMemcpyAsync(a->patches_out_dev, e->p_cat, sizeof(bf16) * Mp * Dv, cudaMemcpyDeviceToDevice, st));
+  const bf16* proj_out;
+  if (e->n_proj == 3) {
+    OVLA_TRY(linear(e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, 4LL * Dv, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e->p_1, 4LL * Dv, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e->p_2, D, e->pj_w[2], Mp, kModeBf16, e->p_3, D, e->pj_b[2].ptr, nullptr, nullptr, 0, 0, 0, st));
+    proj_out = e->p_3;
+  } else {
+    OVLA_TRY(linear(e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, D, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e->p_1, D, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 0, 0, st));
+    proj_out = e->p_2;
+  }
+  if (a->projector_out_dev)
+    CUDA_TRY(cudaMemcpyAsync(a->projector_out_dev, proj_out, sizeof(bf16) * Mp * D, cudaMemcpyDeviceToDevice, st));
+
+  // ---- splice + prefill
+  OVLA_TRY(embed_splice_launch(a->input_ids_dev, B, P, e->embed.ptr, d.vocab, proj_out, np, D, e->l_x, e->err_flag, st));
+  OVLA_TRY(run_llm_layers(e, B, T, 0, a, true, st));
+  if (a->pool_len > 0 && a->pooled_out_dev)
+    CUDA_TRY(cudaMemcpyAsync(a->pooled_out_dev, e->pooled, sizeof(float) * (d.llm_layers + 1LL) * B * D,
+                             cudaMemcpyDeviceToDevice, st));
+
+  // ---- greedy decode: lm_head on the last position only, argmax, then cached single-token steps
+  for (int s = 0; s < n_new; ++s) {
+    const bf16* last = (s == 0) ? e->l_h + 1LL * (T - 1) * D : e->l_h;
+    const long long ld_last = (s == 0) ? 1LL * T * D : D;
+    float* lg = a->step_logits_out_dev ? a->step_logits_out_dev + 1LL * s * B * d.vocab : e->logits;
+    // HF: logits = lm_head(h) in bf16, then .float()  => fp32 storage of bf16-rounded values
+    OVLA_TRY(linear(last, ld_last, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
+    OVLA_TRY(argmax_launch(lg, d.vocab, B, d.vocab, e->tokens + 1LL * s * B, st));
+    if (s + 1 < n_new) {
+      OVLA_TRY(embed_splice_launch(e->tokens + 1LL * s * B, B, 1, e->embed.ptr, d.vocab, nullptr, 0, D, e->l_x,
+                                   e->err_flag, st));
+      OVLA_TRY(run_llm_layers(e, B, 1, T + s, a, false, st));
+    }
+  }
+  if (n_new > 0 && a->tokens_out_dev) {  // [n_new, B] -> [B, n_new]
+    for (int s = 0; s < n_new; ++s)
+      CUDA_TRY(cudaMemcpy2DAsync(a->tokens_out_dev + s, sizeof(long long) * n_new, e->tokens + 1LL * s * B,
+                                 sizeof(long long), sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const void* px_host, int B, int P, int pool_len,
+                             int pool_mode, int n_new, float* pooled_host, long long* tokens_host, void* stream) {
+  if (!e) return set_error("ovla_run_host: null engine");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const OvlaDims& d = e->d;
+  if (B == 0) return 0;
+  if (B < 0 || B > d.max_batch) return set_error("ovla_run_host: batch %d exceeds max_batch %d", B, d.max_batch);
+  if (P < 1 || P > e->max_P) return set_error("ovla_run_host: prompt length %d out of range [1,%d]", P, e->max_P);
+  if (!ids_host || !px_host) return set_error("ovla_run_host: null input");
+  const long long px_elems = 1LL * B * 3 * d.n_towers * d.image_size * d.image_size;
+  CUDA_TRY(cudaMemcpyAsync(e->in_ids, ids_host, sizeof(long long) * B * P, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(e->in_px, px_host, sizeof(bf16) * px_elems, cudaMemcpyHostToDevice, st));
+  OvlaRunArgs a = {};
+  a.input_ids_dev = e->in_ids;
+  a.pixel_values_dev = e->in_px;
+  a.B = B;
+  a.P = P;
+  a.pool_len = pooled_host ? pool_len : 0;
+  a.pool_mode = pool_mode;
+  a.n_new_tokens = tokens_host ? n_new : 0;
+  a.tokens_out_dev = e->out_tokens;
+  OVLA_TRY(ovla_run(e, &a, st));
+  if (a.pool_len > 0)
+    CUDA_TRY(cudaMemcpyAsync(pooled_host, e->pooled, sizeof(float) * (d.llm_layers + 1LL) * B * d.llm_dim,
+                             cudaMemcpyDeviceToHost, st));
+  if (a.n_new_tokens > 0)
+    CUDA_TRY(cudaMemcpyAsync(tokens_host, e->out_tokens, sizeof(long long) * B * n_new, cudaMemcpyDeviceToHost, st));
+  int err = 0;
+  CUDA_TRY(cudaMemcpyAsync(&err, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (err) {
+    cudaMemset(e->err_flag, 0, sizeof(int));
+    return set_error("ovla_run_host: input_ids contain a token id outside [0, %d)", d.vocab);
+  }
+  return 0;
+}

@@ -1,0 +1,133 @@
+// LayerNorm (timm ViT, eps 1e-6, affine) and Llama RMSNorm -- HBM-bound row kernels, one warp per row,
+// 16-byte loads/stores, the whole row held in registers between the statistics pass and the write.
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace ovla {
+
+static constexpr int kNormMaxChunks = 18;  // 18 * 32 lanes * 8 elems = 4608 >= 4096 / 4304
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// MODE 0: LayerNorm -> bf16( (x-mean)*rstd*w + b )      (torch.nn.LayerNorm on bf16: fp32 math, one rounding)
+// MODE 1: Llama RMSNorm -> bf16( w * bf16(x*rsqrt(mean(x^2)+eps)) )   (transformers LlamaRMSNorm.forward)
+template <int MODE, int CHUNKS>
+__global__ void __launch_bounds__(128) norm_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                        const __nv_bfloat16* __restrict__ w,
+                                                        const __nv_bfloat16* __restrict__ b, float eps,
+                                                        __nv_bfloat16* __restrict__ out, long long ldo, int rows,
+                                                        int D) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* xr = x + static_cast<long long>(row) * ldx;
+  uint4 v[CHUNKS];
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      v[c] = *reinterpret_cast<const uint4*>(xr + col);
+      const uint32_t u[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(u[i]);
+        sum += f.x + f.y;
+        sq += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  float mean = 0.f, rstd;
+  if (MODE == 0) {
+    mean = warp_sum(sum) / D;
+    float var = 0.f;  // second pass over registers: sum (x-mean)^2, as torch does
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        const uint32_t u[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(u[i]);
+          var += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
+      }
+    }
+    rstd = rsqrtf(warp_sum(var) / D + eps);
+  } else {
+    rstd = rsqrtf(warp_sum(sq) / D + eps);
+  }
+  __nv_bfloat16* orow = out + static_cast<long long>(row) * ldo;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(w + col);
+      const uint32_t u[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+      const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+      if (MODE == 0) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(b + col);
+        const uint32_t bu[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(u[i]), wf = unpack_bf16(wu[i]), bf = unpack_bf16(bu[i]);
+          o[i] = pack_bf16((f.x - mean) * rstd * wf.x + bf.x, (f.y - mean) * rstd * wf.y + bf.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(u[i]), wf = unpack_bf16(wu[i]);
+          o[i] = pack_bf16(wf.x * bf16_round(f.x * rstd), wf.y * bf16_round(f.y * rstd));
+        }
+      }
+      *reinterpret_cast<uint4*>(orow + col) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int MODE>
+static int norm_dispatch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out,
+                         long long ldo, int rows, int D, cudaStream_t st) {
+  if (D % 8) return set_error("norm: D=%d must be a multiple of 8", D);
+  const int chunks = (D + 255) / 256;
+  if (chunks > kNormMaxChunks) return set_error("norm: D=%d too large", D);
+  const dim3 grid((rows + 3) / 4), block(128);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto W = static_cast<const __nv_bfloat16*>(w);
+  auto B = static_cast<const __nv_bfloat16*>(b);
+  auto O = static_cast<__nv_bfloat16*>(out);
+#define OVLA_NORM_CASE(C)                                                                        \
+  if (chunks <= C) {                                                                             \
+    norm_rows_kernel<MODE, C><<<grid, block, 0, st>>>(X, ldx, W, B, eps, O, ldo, rows, D);       \
+    CUDA_TRY(cudaGetLastError());                                                                \
+    count_launch();                                                                              \
+    return 0;                                                                                    \
+  }
+  OVLA_NORM_CASE(1)
+  OVLA_NORM_CASE(2)
+  OVLA_NORM_CASE(5)
+  OVLA_NORM_CASE(16)
+  OVLA_NORM_CASE(18)
+#undef OVLA_NORM_CASE
+  return set_error("norm: unreachable");
+}
+
+int layernorm_launch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
+                     int rows, int D, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  return norm_dispatch<0>(x, ldx, w, b, eps, out, ldo, rows, D, st);
+}
+
+int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void* out, long long ldo, int rows, int D,
+                   cudaStream_t st) {
+  if (rows <= 0) return 0;
+  return norm_dispatch<1>(x, ldx, w, nullptr, eps, out, ldo, rows, D, st);
+}
+
+}  // namespace ovla

@@ -10,8 +10,41 @@ namespace ovla {
 
 int num_sms();
 
-// gemm.cu
+// gemm.cu -- tcgen05 GEMM
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
                 const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream);
+// gemv.cu -- M <= 8 weight streaming
+int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, int mode,
+                const GemmEpi& epi, cudaStream_t st);
+
+// norm.cu
+int layernorm_launch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
+                     int rows, int D, cudaStream_t st);
+int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void* out, long long ldo, int rows, int D,
+                   cudaStream_t st);
+
+// attention.cu
+int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
+                      int Tq, int Tk, int head_dim, int causal, cudaStream_t st);
+int decode_attn_launch(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
+                       int Tmax, int ctx, void* out, long long o_ld, cudaStream_t st);
+
+// elementwise.cu
+int im2col_launch(const void* px, int B, int c_total, int c0, int H, int W, int patch, int Kpad, void* out,
+                  cudaStream_t st);
+int assemble_tokens_launch(const void* patch, const void* pos, const void* cls, const void* reg, int B, int np,
+                           int n_prefix, int D, void* tokens, cudaStream_t st);
+int copy_rows_launch(const void* src, long long src_batch, long long src_ld, int srow0, void* dst, long long dst_batch,
+                     long long dst_ld, int dcol0, int B, int rows, int cols, cudaStream_t st);
+int embed_splice_launch(const void* ids, int B, int P, const void* E, int vocab, const void* proj, int np, int D,
+                        void* x, int* err_flag, cudaStream_t st);
+int rope_kv_launch(void* qkv, int B, int T, int H, int hd, int pos0, const void* cos_t, const void* sin_t, void* kc,
+                   void* vc, int Tmax, cudaStream_t st);
+int pool_tokens_launch(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                       float* out, long long out_batch_stride, cudaStream_t st);
+int argmax_launch(const float* x, long long ld, int rows, int n, long long* out, cudaStream_t st);
+int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_size, const double* centers,
+                        int n_centers, const double* q01, const double* q99, const unsigned char* mask, double* out,
+                        cudaStream_t st);
 
 }  // namespace ovla

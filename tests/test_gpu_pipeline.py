@@ -1,0 +1,138 @@
+"""GPU parity: the fused CUDA pass (through the C ABI) against the CPU oracle on shared seeded weights.
+
+Tolerance policy (written here): for every checked tensor, our bf16 result must stay within
+c = 2x the error envelope of the oracle's own bf16 evaluation against the oracle in fp32 (rel-L2 and max-abs,
+plus a small absolute floor); token ids are compared exactly where the oracle's bf16 and fp32 runs agree on them.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import envelope_ok, pair, rel_l2, to_f32
+from oracle import openvla_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(kind="tiny", fused=True, B=3, P=12, llm_layers=2, depth=(3, 3), seed=0):
+    from openvla_probe_b200.modeling_prismatic import from_state_dict
+
+    od, pc = pair(kind, fused=fused, llm_layers=llm_layers, depth=depth)
+    W = O.make_weights(od, seed=seed)
+    stats = {"synthetic": {"action": O.default_stats()}}
+    import dataclasses
+
+    pc = dataclasses.replace(pc, norm_stats=stats)
+    model = from_state_dict(pc, W, max_batch=max(B, 1), max_prompt_len=P + 2)
+    ids, px = O.make_inputs(od, B, prompt_len=P, seed=seed + 1)
+    return od, pc, W, model, ids, px
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_forward_hidden_states_and_logits(fused):
+    od, pc, W, model, ids, px = _build(fused=fused, B=2, P=10)
+    out = model.forward(input_ids=ids.cuda(), pixel_values=px.cuda(), output_hidden_states=True,
+                        output_projector_features=True)
+    with torch.no_grad():
+        ref32 = O.multimodal_forward(to_f32(W), od, ids, px, dtype=torch.float32)
+        ref16 = O.multimodal_forward(W, od, ids, px, dtype=torch.bfloat16)
+    assert len(out.hidden_states) == od.llm_layers + 1
+    ok, info = envelope_ok(out.projector_features.float().cpu(), ref32.projector_features, ref16.projector_features.float())
+    assert ok, f"projector: {info}"
+    for i in range(od.llm_layers + 1):
+        ok, info = envelope_ok(out.hidden_states[i].float().cpu(), ref32.hidden_states[i], ref16.hidden_states[i].float())
+        assert ok, f"hidden[{i}]: {info}"
+    ok, info = envelope_ok(out.logits.cpu(), ref32.logits, ref16.logits)
+    assert ok, f"logits: {info}"
+    # hidden_states[0] is the spliced embedding: [BOS | patches | text[1:]] -- exact copy semantics
+    emb = O.embed(W, ids, torch.bfloat16)
+    hs0 = out.hidden_states[0].cpu()
+    assert torch.equal(hs0[:, 0], emb[:, 0]) and torch.equal(hs0[:, od.n_patches + 1:], emb[:, 1:])
+
+
+def test_vision_backbone_patches():
+    od, pc, W, model, ids, px = _build(B=2, P=6)
+    r = model.engine.run(ids, px, 0, 0, 0, want_patches=True)
+    with torch.no_grad():
+        ref32 = O.vision_backbone(to_f32(W), od, px.float())
+        ref16 = O.vision_backbone(W, od, px)
+    ok, info = envelope_ok(r["patches"].float().cpu(), ref32, ref16.float())
+    assert ok, info
+    # concat order DINO || SigLIP (modeling_prismatic.py:123)
+    d0 = od.towers[0].dim
+    assert rel_l2(r["patches"][..., :d0].float().cpu(), ref32[..., :d0]) < 0.05
+    assert rel_l2(r["patches"][..., d0:].float().cpu(), ref32[..., d0:]) < 0.05
+
+
+@pytest.mark.parametrize("pooling", ["mean", "final"])
+def test_capture_and_action_single_pass_equals_two_pass(pooling):
+    od, pc, W, model, ids, px = _build(B=3, P=9)
+    layers = list(range(od.llm_layers + 1))
+    embeds, actions = model.predict_action_and_capture(ids, unnorm_key="synthetic", layer_indices=layers + [-1],
+                                                       pooling_method=pooling, pixel_values=px)
+    stats = O.default_stats()
+    with torch.no_grad():
+        e32, a32 = O.get_vla_action(to_f32(W), od, ids, px, stats, layers, pooling, dtype=torch.float32)
+        e16, a16 = O.get_vla_action(W, od, ids, px, stats, layers, pooling, dtype=torch.bfloat16)
+    assert actions.shape == (3, 7) and actions.dtype == np.float64
+    for L in layers:
+        assert embeds[L].shape == (3, od.llm_dim) and embeds[L].dtype == np.float32
+        ok, info = envelope_ok(embeds[L], e32[L], e16[L])
+        assert ok, f"pooled layer {L} ({pooling}): {info}"
+    assert np.array_equal(embeds[-1], embeds[od.llm_layers])
+
+
+def test_tokens_match_oracle_given_identical_logits_and_agreement_rate():
+    od, pc, W, model, ids, px = _build(B=4, P=8)
+    ids29 = torch.cat([ids, torch.full((4, 1), 29871)], 1)
+    r = model.engine.run(ids29, px, 0, 0, 7, want_logits=True)
+    tokens = r["tokens"].cpu()
+    logits = r["step_logits"].cpu()           # [7, B, V]
+    # bit-exact argmax given identical logits (lowest index on ties)
+    assert torch.equal(tokens, torch.argmax(logits, dim=-1).t())
+    with torch.no_grad():
+        seq16, lg16, _ = O.greedy_generate(W, od, ids29, px, 7, dtype=torch.bfloat16, stop_on_eos=False)
+        seq32, lg32, _ = O.greedy_generate(to_f32(W), od, ids29, px, 7, dtype=torch.float32, stop_on_eos=False)
+    # first generated token: same prefill => envelope on the logits
+    ok, info = envelope_ok(logits[0], lg32[0], lg16[0])
+    assert ok, info
+    agree = (tokens == seq16[:, -7:]).float().mean().item()
+    print(f"action-token agreement vs bf16 oracle: {agree:.3f}")
+
+
+def test_batch_invariance():
+    od, pc, W, model, ids, px = _build(B=4, P=8)
+    (a_all, t_all), pooled_all = model._predict(ids, "synthetic", capture=True, pixel_values=px, return_tokens=True)
+    for b in (0, 3):
+        (a_b, t_b), pooled_b = model._predict(ids[b:b + 1], "synthetic", capture=True, pixel_values=px[b:b + 1],
+                                              return_tokens=True)
+        assert np.array_equal(t_all[b], t_b[0])
+        assert np.array_equal(a_all[b], a_b)
+        assert np.allclose(pooled_all[:, b], pooled_b[:, 0], rtol=0, atol=1e-6)
+
+
+def test_host_and_device_entry_points_agree():
+    od, pc, W, model, ids, px = _build(B=2, P=8)
+    a_host, p_host = model._predict(ids, "synthetic", capture=True, pixel_values=px)
+    a_dev, p_dev = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda())
+    assert np.array_equal(a_host, a_dev) and np.array_equal(p_host, p_dev)
+
+
+def test_error_behaviour():
+    from openvla_probe_b200 import _lib
+
+    od, pc, W, model, ids, px = _build(B=2, P=8)
+    with pytest.raises(AssertionError):
+        model.predict_action(ids, unnorm_key="nope", pixel_values=px)
+    with pytest.raises(ValueError):
+        model.predict_action(ids, unnorm_key="synthetic", pixel_values=px[:1])
+    with pytest.raises(_lib.OvlaError):
+        big = torch.cat([ids] * 3)
+        model.predict_action(big, unnorm_key="synthetic", pixel_values=torch.cat([px] * 3))   # > max_batch
+    bad = ids.clone()
+    bad[0, 3] = 40000
+    with pytest.raises(_lib.OvlaError):
+        model.predict_action(bad, unnorm_key="synthetic", pixel_values=px)
+    # empty batch
+    a = model.predict_action(ids[:0], unnorm_key="synthetic", pixel_values=px[:0])
+    assert a.shape == (0, 7)
