@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native OpenVLA predict_action + all-layer hidden-state capture path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU (oracle port)
+
+A "step" = one fused pass over one batch of synthetic observations: bs=256 per GPU (BASELINE.json configs[2]),
+224-px frames, 31-token LIBERO-style prompt (+29871 => T = 288), 7 greedy action tokens, 33 mean-pooled layers.
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "actions/sec w/ all-layer hidden capture (openvla-7b predict_action, 33 pooled layers)"
+UNIT = "actions/s"
+N_LAYERS_CAPTURED = 33
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="observations per GPU per step")
+    ap.add_argument("--prompt-len", type=int, default=31, help="prompt ids incl. BOS, before 29871 is appended")
+    ap.add_argument("--config", default="openvla-7b", choices=["openvla-7b", "siglip-7b", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bs1", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_inputs(cfg, batch: int, prompt_len: int, seed: int):
+    """DummyDataset-style observations (prismatic/vla/datasets/datasets.py:207): uint8 frames normalised per tower
+    exactly as PrismaticImageProcessor does, bf16, channel-stacked; prompt = [BOS] + random text ids."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (batch, cfg.image_size, cfg.image_size, 3), dtype=np.uint8)
+    x = torch.from_numpy(img).permute(0, 3, 1, 2).float() / 255.0
+    stats = [((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    if not cfg.use_fused_vision_backbone:
+        stats = stats[1:]
+    px = torch.cat([(x - torch.tensor(m).view(1, 3, 1, 1)) / torch.tensor(s).view(1, 3, 1, 1) for m, s in stats], 1)
+    ids = np.concatenate([np.ones((batch, 1), np.int64), rng.integers(3, 31744, (batch, prompt_len - 1))], 1)
+    return torch.from_numpy(ids), px.to(torch.bfloat16).contiguous()
+
+
+def algorithmic_flops_per_action(cfg, T: int) -> float:
+    """2*M*N*K of every linear (discarded last ViT blocks skipped), causal attention counted at half,
+    lm_head on one row; + the 6 cached decode steps."""
+    f = 0.0
+    np_ = cfg.n_patches
+    for t in cfg.towers:
+        N = np_ + t.n_prefix
+        f += 2.0 * np_ * t.dim * 3 * cfg.patch ** 2
+        per = 2.0 * N * (3 * t.dim * t.dim + t.dim * t.dim + 2 * t.dim * t.mlp) + 4.0 * N * N * t.dim
+        f += per * (t.depth - 1)
+    vd, D = cfg.vision_dim, cfg.text_config.hidden_size
+    if cfg.use_fused_vision_backbone:
+        f += 2.0 * np_ * (vd * 4 * vd + 4 * vd * D + D * D)
+    else:
+        f += 2.0 * np_ * (vd * D + D * D)
+    tc = cfg.text_config
+    lin = 4 * D * D + 3 * D * tc.intermediate_size
+    f += tc.num_hidden_layers * (2.0 * T * lin + 2.0 * T * T * D) + 2.0 * D * tc.vocab_size
+    f += 6 * (tc.num_hidden_layers * 2.0 * lin + 2.0 * D * tc.vocab_size)
+    return f
+
+
+# ----------------------------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_reference_run(cfg_name: str, prompt_len: int, steps: int, warmup: int, budget_s: float):
+    """The reference's own algorithm for the path on the host CPU: oracle port (oracle/openvla_oracle.py) of
+    get_vla_action's TWO passes (capture forward + predict_action generate), fp32, bs=1, all host threads."""
+    from oracle import openvla_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = {"openvla-7b": O.OPENVLA_7B, "siglip-7b": O.SIGLIP_7B, "tiny": O.tiny_dims()}[cfg_name]
+    t0 = time.time()
+    shapes = O.weight_shapes(d)
+    need_gb = sum(int(np.prod(s)) for s in shapes.values()) * 4 / 1e9
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 1e9
+    except Exception:
+        avail_gb = 0.0
+    distinct = avail_gb > need_gb * 1.4 + 8.0          # else share one buffer per shape (same FLOPs, less RAM)
+    W = {}
+    cache = {}
+    for name, shape in shapes.items():                 # values do not affect CPU time
+        key = (shape, len(shape) == 1 and not name.endswith("bias"))
+        if key not in cache:
+            w = torch.empty(shape, dtype=torch.float32)
+            if key[1]:
+                w.fill_(1.0)
+            else:
+                w.uniform_(-0.035, 0.035)
+            cache[key] = w
+            W[name] = w
+        else:
+            W[name] = cache[key].clone() if distinct else cache[key]
+    init_s = time.time() - t0
+    ids, px = O.make_inputs(d, 1, prompt_len=prompt_len, seed=1)
+    stats = O.default_stats()
+    layers = list(range(d.llm_layers + 1))
+    times = []
+    with torch.no_grad():
+        for _ in range(min(warmup, 1)):                # one untimed pass at most: a pass takes tens of seconds
+            O.get_vla_action(W, d, ids, px, stats, layers, "mean", dtype=torch.float32)
+        t_begin = time.time()
+        for _ in range(steps):
+            if times and (time.time() - t_begin) + times[-1] > budget_s:
+                break
+            t1 = time.time()
+            O.get_vla_action(W, d, ids, px, stats, layers, "mean", dtype=torch.float32)
+            times.append(time.time() - t1)
+    ms = 1e3 * sum(times) / len(times)
+    return {"ms_per_action": ms, "actions_per_s": 1e3 / ms, "steps_timed": len(times), "init_s": init_s,
+            "cores": os.cpu_count() or 1, "distinct_weights": distinct}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.config, args.prompt_len, max(1, args.steps), max(1, args.warmup), args.cpu_budget_s)
+    sample = ("1 observation per step (bs=1), full get_vla_action two-pass order (capture forward + 7-token greedy "
+              "generate), fp32, all host threads; "
+              + ("distinct weight buffers" if r["distinct_weights"] else "equal-shaped weights share one buffer (host RAM)"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["actions_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_action"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, "
+                               f"T={256 + args.prompt_len + 1}, bs=1 sample on host CPU"},
+        "cpu_baseline": {"value": r["actions_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["actions_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import ctypes as C
+    import dataclasses
+
+    import torch.distributed as dist
+
+    from openvla_probe_b200 import _lib, config as cfgmod, weights
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    base = {"openvla-7b": cfgmod.openvla_7b, "siglip-7b": cfgmod.siglip_7b, "tiny": cfgmod.tiny}[args.config]()
+    stats = {"synthetic": {"action": {"q01": np.linspace(-0.9, -0.3, 7).tolist(), "q99": np.linspace(0.4, 1.0, 7).tolist(),
+                                      "mask": [True] * 6 + [False]}}}
+    cfg = dataclasses.replace(base, norm_stats=stats)
+    B, P0 = args.batch, args.prompt_len
+    T = cfg.n_patches + P0 + 1
+    model = OpenVLAForActionPrediction(cfg, max_batch=B, max_prompt_len=P0 + 1, device=local)
+    weights.bind_random(model, seed=0)
+    ids, px = synthetic_inputs(cfg, B, P0, seed=1 + rank)
+    ids29 = torch.cat([ids, torch.full((B, 1), 29871, dtype=torch.int64)], 1)
+    ids_dev, px_dev = ids29.cuda(), px.cuda()
+    px_pin = px.pin_memory()
+    pool_len = cfg.n_patches + P0
+    n_act = 7
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return model.engine.run(ids_dev, px_dev, pool_len, 0, n_act)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    # ---- device-resident timing (value)
+    cat_n = (C.c_longlong * 7)(); cat_ms = (C.c_double * 7)(); cat_fl = (C.c_double * 7)(); cat_by = (C.c_double * 7)()
+    lib.ovla_profile_enable(1)
+    lib.ovla_reset_launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.ovla_launch_count())
+    lib.ovla_profile_enable(0)
+    _lib.check(lib.ovla_profile_collect(cat_n, cat_ms, cat_fl, cat_by))
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    for _ in range(2):
+        model.predict_action_and_capture(ids, unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)),
+                                         pixel_values=px_pin)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        embeds, actions = model.predict_action_and_capture(
+            ids, unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)), pixel_values=px_pin)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(t.item()) / args.steps / 1e3)
+    L, D = cfg.text_config.num_hidden_layers, cfg.text_config.hidden_size
+    h2d = B * (P0 + 1) * 8 + px.numel() * 2
+    d2h = (L + 1) * B * D * 4 + B * n_act * 8
+
+    # ---- bs=1 latency (p50), device-resident and end-to-end
+    bs1 = None
+    if not args.no_bs1:
+        i1, p1 = ids_dev[:1].contiguous(), px_dev[:1].contiguous()
+        for _ in range(3):
+            model.engine.run(i1, p1, pool_len, 0, n_act)
+        lat = []
+        for _ in range(15):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); model.engine.run(i1, p1, pool_len, 0, n_act); b.record(); torch.cuda.synchronize()
+            lat.append(a.elapsed_time(b))
+        lat_e2e = []
+        px1 = px[:1].contiguous().pin_memory()
+        for _ in range(15):
+            t0 = time.perf_counter()
+            model.predict_action_and_capture(ids[:1], unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)),
+                                             pixel_values=px1)
+            lat_e2e.append((time.perf_counter() - t0) * 1e3)
+        bs1 = {"p50_ms": statistics.median(lat), "e2e_p50_ms": statistics.median(lat_e2e)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    names = ["gemm_tcgen05", "gemv", "flash_attn", "decode_attn", "norm", "pool", "other"]
+    cats = {n: {"launches": int(cat_n[i]), "ms_per_step": cat_ms[i] / args.steps,
+                "tflops": (cat_fl[i] / (cat_ms[i] * 1e-3) / 1e12) if cat_ms[i] > 0 and cat_fl[i] > 0 else None,
+                "gbs": (cat_by[i] / (cat_ms[i] * 1e-3) / 1e9) if cat_ms[i] > 0 and cat_by[i] > 0 else None}
+            for i, n in enumerate(names)}
+    g = cats["gemm_tcgen05"]
+    gemm_tf = g["tflops"] or 0.0
+    roofline = {
+        "kernel": "gemm_tcgen05_kernel (all ViT / projector / Llama linears of the step)",
+        "bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["launches"] / args.steps,
+        "traffic": None,
+        "decode_attn_hbm": {"achieved_gbs": cats["decode_attn"]["gbs"], "peak_gbs": peaks["hbm_gbs"],
+                            "frac": (cats["decode_attn"]["gbs"] or 0.0) / peaks["hbm_gbs"]},
+    }
+    step_tf = algorithmic_flops_per_action(cfg, T) * B / (ms_step * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, "
+                               f"bs={B}/GPU, 224px frames, T={T} (256 patches + {P0 + 1} prompt ids), 7 greedy action tokens",
+                   "global_batch": world * B, "weights": "random-init N(0,0.02) bf16, replicated per GPU",
+                   "l2": "per-step working set (>40 GB of activations + 15 GB weights) exceeds the 126 MB L2; no flush needed",
+                   "parallelism": f"dp{world} (observations sharded, no data-path collective)"},
+        "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / peaks["tf_sustained"],
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "roofline": roofline, "kernel_breakdown": cats,
+    }
+    if bs1:
+        line["bs1_latency"] = bs1
+    if world == 1 and not args.no_cpu_baseline:
+        model.engine.close()
+        del model
+        torch.cuda.empty_cache()
+        try:
+            r = cpu_reference_run(args.config, P0, 1, 0, 90.0)
+            line["cpu_baseline"] = {
+                "value": r["actions_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                "sample": "1 observation (bs=1), full two-pass get_vla_action order, fp32, all host threads, "
+                          f"{r['steps_timed']} timed pass(es) of {r['ms_per_action'] / 1e3:.1f} s",
+            }
+        except Exception as ex:  # noqa: BLE001 -- the baseline must never take the GPU number down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {type(ex).__name__}: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

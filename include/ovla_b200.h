@@ -27,6 +27,14 @@ const char* ovla_last_error(void);
 long long ovla_launch_count(void);
 void ovla_reset_launch_count(void);
 
+/* Live kernel timing (bench.py roofline): when enabled, each kernel launch is bracketed by CUDA events recorded on
+ * its launch stream.  ovla_profile_collect synchronises those events and sums, per category, the number of launches,
+ * the device milliseconds, and the algorithmic flops / bytes the launches were asked to do; it then clears the log. */
+enum { OVLA_CAT_GEMM = 0, OVLA_CAT_GEMV, OVLA_CAT_FLASH_ATTN, OVLA_CAT_DECODE_ATTN, OVLA_CAT_NORM, OVLA_CAT_POOL,
+       OVLA_CAT_OTHER, OVLA_NUM_CAT };
+void ovla_profile_enable(int on);
+int ovla_profile_collect(long long* launches, double* ms, double* flops, double* bytes);
+
 /* ------------------------------------------------------------------ operators (device pointers)
  * Building blocks of PrismaticForConditionalGeneration.forward (prismatic/extern/hf/modeling_prismatic.py:291-447),
  * exposed one by one so that parity tests can check each kernel against the CPU oracle.            */

@@ -41,6 +41,12 @@ int ovla_abi_version(void) { return OVLA_ABI_VERSION; }
 const char* ovla_last_error(void) { return last_error(); }
 long long ovla_launch_count(void) { return launch_count(); }
 void ovla_reset_launch_count(void) { reset_launch_count(); }
+void ovla_profile_enable(int on) { prof_enable(on != 0); }
+int ovla_profile_collect(long long* launches, double* ms, double* flops, double* bytes) {
+  static_assert(static_cast<int>(OVLA_NUM_CAT) == static_cast<int>(kNumCat), "category enums out of sync");
+  if (!launches || !ms || !flops || !bytes) return set_error("ovla_profile_collect: null argument");
+  return prof_collect(launches, ms, flops, bytes);
+}
 
 int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               int kind, void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, int tile_n, int cta_group,

@@ -236,6 +236,7 @@ static int flash_launch_t(const void* Q, const void* K, const void* V, void* O, 
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid((Tq + 63) / 64, H, B);
+  ProfScope prof(kCatFlash, (CAUSAL ? 2.0 : 4.0) * B * H * Tq * Tk * HD, 2.0 * B * H * HD * (2.0 * Tq + 2.0 * Tk), st);
   kern<<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K),
                                static_cast<const __nv_bfloat16*>(V), static_cast<__nv_bfloat16*>(O), s, Tq, Tk,
                                scale_log2);
@@ -363,6 +364,7 @@ int decode_attn_launch(const void* q, long long q_ld, const void* kc, const void
   const int smem = (ctx > 8 * 128 ? ctx : 8 * 128) * sizeof(float);
   if (smem > 48 * 1024) return set_error("decode attention: ctx=%d too long", ctx);
   dim3 grid(H, B);
+  ProfScope prof(kCatDecodeAttn, 4.0 * B * H * ctx * head_dim, 4.0 * B * H * ctx * head_dim + 4.0 * B * H * head_dim, st);
   decode_attn_kernel<128><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(q), q_ld,
                                                    static_cast<const __nv_bfloat16*>(kc),
                                                    static_cast<const __nv_bfloat16*>(vc), Tmax, ctx,

@@ -216,6 +216,7 @@ int rope_kv_launch(void* qkv, int B, int T, int H, int hd, int pos0, const void*
   if (pos0 + T > Tmax) return set_error("rope: position %d exceeds KV capacity %d", pos0 + T, Tmax);
   const long long total = static_cast<long long>(B) * T * H * (hd / 16);
   if (total <= 0) return 0;
+  ProfScope prof(kCatOther, 0.0, 12.0 * B * T * H * hd, st);
   rope_kv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
       static_cast<__nv_bfloat16*>(qkv), T, H, hd, pos0, static_cast<const __nv_bfloat16*>(cos_t),
       static_cast<const __nv_bfloat16*>(sin_t), static_cast<__nv_bfloat16*>(kc), static_cast<__nv_bfloat16*>(vc),
@@ -282,6 +283,7 @@ int pool_tokens_launch(const void* x, long long batch_stride, long long ld, int 
   if (n_rows <= 0) return set_error("pool_tokens: empty token range");
   if (D % 8) return set_error("pool_tokens: D must be a multiple of 8");
   dim3 grid((D + 255) / 256, B);
+  ProfScope prof(kCatPool, 0.0, (mode == 0 ? 2.0 * B * n_rows * D : 2.0 * B * D) + 4.0 * B * D, st);
   pool_tokens_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), batch_stride, ld, n_rows, D, mode,
                                           out, out_batch_stride);
   CUDA_TRY(cudaGetLastError());

@@ -64,6 +64,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSh
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfScope prof(kCatGemm, 2.0 * s.M * s.N * s.K, 0.0, stream);
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, s, e));
   count_launch();
   return 0;

@@ -119,6 +119,7 @@ static int gemv_dispatch(const void* x, long long ldx, const void* W, long long 
   if (blocks > max_blocks) blocks = max_blocks;
   auto X = static_cast<const __nv_bfloat16*>(x);
   auto Wp = static_cast<const __nv_bfloat16*>(W);
+  ProfScope prof(kCatGemv, 2.0 * M * N * K, 2.0 * N * K + 2.0 * M * (K + n_out), st);
   if (M <= 1) gemv_kernel<1, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
   else if (M <= 2) gemv_kernel<2, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
   else if (M <= 4) gemv_kernel<4, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);

@@ -12,6 +12,27 @@ void count_launch(int n = 1);
 long long launch_count();
 void reset_launch_count();
 
+// Live kernel timing for bench.py's roofline: when enabled, every launch site brackets its kernel with CUDA events
+// recorded on the launch stream; prof_collect() synchronises and sums per category.
+enum ProfCat : int { kCatGemm = 0, kCatGemv, kCatFlash, kCatDecodeAttn, kCatNorm, kCatPool, kCatOther, kNumCat };
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_begin(int cat, double flops, double bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+// out arrays of kNumCat: launches, milliseconds, flops, bytes. Clears the records.
+int prof_collect(long long* launches, double* ms, double* flops, double* bytes);
+
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cat, double flops, double bytes, cudaStream_t s) : st(s), on(prof_enabled()) {
+    if (on) prof_begin(cat, flops, bytes, st);
+  }
+  ~ProfScope() {
+    if (on) prof_end(st);
+  }
+};
+
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

@@ -98,6 +98,7 @@ static int norm_dispatch(const void* x, long long ldx, const void* w, const void
   const int chunks = (D + 255) / 256;
   if (chunks > kNormMaxChunks) return set_error("norm: D=%d too large", D);
   const dim3 grid((rows + 3) / 4), block(128);
+  ProfScope prof(kCatNorm, 0.0, 4.0 * rows * D, st);
   auto X = static_cast<const __nv_bfloat16*>(x);
   auto W = static_cast<const __nv_bfloat16*>(w);
   auto B = static_cast<const __nv_bfloat16*>(b);

@@ -203,8 +203,11 @@ class OpenVLAForActionPrediction:
             # reference-facing host path: pinned staging, H2D + compute + D2H inside one native call
             ids_p = self._pinned("ids", (B, P), torch.int64)
             ids_p.copy_(ids)
-            px_p = self._pinned("px", tuple(pixel_values.shape), torch.bfloat16)
-            px_p.copy_(pixel_values)
+            if pixel_values.dtype == torch.bfloat16 and pixel_values.is_contiguous() and pixel_values.is_pinned():
+                px_p = pixel_values                   # caller already holds the frame batch in pinned memory
+            else:
+                px_p = self._pinned("px", tuple(pixel_values.shape), torch.bfloat16)
+                px_p.copy_(pixel_values)
             tok_p = self._pinned("tok", (B, n_act), torch.int64)
             pool_p = self._pinned("pool", (tc.num_hidden_layers + 1, B, tc.hidden_size), torch.float32) if capture else None
             self.engine.run_host(ids_p, px_p, pool_len, pool_mode, n_act, pool_p, tok_p)
