@@ -1,0 +1,141 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/ovla_b200.h declares (no compute
+calls without a GPU), and the host logic of the drop-in surface (29871 rule, EOS replay, error conventions)."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from openvla_probe_b200 import _lib
+    from openvla_probe_b200.build import build
+
+    build(verbose=False)
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "ovla_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ovla_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ovla_b200.h but not exported by libovla_b200.so"
+    assert lib.ovla_abi_version() == 1
+
+
+def test_library_contains_blackwell_instructions():
+    """The shipped binary is sm_100a SASS with tcgen05 / TMA / TMEM instructions (no PTX-JIT, no fallback arch)."""
+    import shutil
+    import subprocess
+
+    from openvla_probe_b200 import _lib
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.lib_path())], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback_without_gpu():
+    from openvla_probe_b200 import _lib, config
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.OvlaError):
+        OpenVLAForActionPrediction(config.tiny())
+
+
+def _bare_model():
+    """Host-logic-only instance (no engine): the methods under test never touch the device."""
+    from openvla_probe_b200 import config
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    stats = {"a": {"action": {"q01": [0.0] * 7, "q99": [1.0] * 7}}, "b": {"action": {"q01": [0.0] * 3, "q99": [1.0] * 3}}}
+    m = object.__new__(OpenVLAForActionPrediction)
+    m.config = dataclasses.replace(config.tiny(), norm_stats=stats)
+    m.norm_stats = stats
+    return m
+
+
+def test_unnorm_key_conventions():
+    m = _bare_model()
+    with pytest.raises(AssertionError):
+        m.get_action_dim(None)                 # more than one dataset and no key (modeling_prismatic.py:539-546)
+    with pytest.raises(AssertionError):
+        m.get_action_dim("missing")
+    assert m.get_action_dim("a") == 7 and m.get_action_dim("b") == 3
+    assert m.get_action_stats("b")["q99"] == [1.0] * 3
+
+
+def test_append_29871_is_batch_wide():
+    m = _bare_model()
+    ids = torch.tensor([[1, 5, 29871], [1, 6, 29871]])
+    assert m._append_empty(ids).shape == (2, 3)
+    ids[0, -1] = 9
+    out = m._append_empty(ids)
+    assert out.shape == (2, 4) and out[:, -1].tolist() == [29871, 29871]
+
+
+def test_eos_replay_matches_hf_semantics():
+    m = _bare_model()
+    ids = torch.arange(10, 20).view(1, 10)
+    toks = np.array([[7, 8, 2, 4, 5, 6, 7]])
+    got = m._finish_sequences(ids, toks, 7)
+    assert got.tolist() == [[16, 17, 18, 19, 7, 8, 2]]
+    toks = np.array([[7, 8, 9, 4, 5, 6, 3]])
+    assert m._finish_sequences(ids, toks, 7).tolist() == toks.tolist()
+
+
+def test_input_validation_errors():
+    m = _bare_model()
+    ids = torch.ones(2, 5, dtype=torch.long)
+    px = torch.zeros(2, 6, 56, 56)
+    with pytest.raises(ValueError):
+        m._check_inputs(ids, px[:1], None)
+    with pytest.raises(ValueError):
+        m._check_inputs(ids, px[:, :3], None)
+    mask = torch.ones(2, 5, dtype=torch.long)
+    mask[1, -1] = 0
+    with pytest.raises(ValueError):
+        m._check_inputs(ids, px, mask)
+    m._check_inputs(ids, px, torch.ones(2, 5))
+
+
+def test_state_dict_schema_matches_oracle_and_golden():
+    from helpers import pair
+    from openvla_probe_b200 import weights
+    from oracle import openvla_oracle as O
+
+    for kind, fused in (("tiny", True), ("tiny", False), ("openvla-7b", True), ("siglip-7b", False)):
+        od, pc = pair(kind, fused=fused)
+        assert weights.state_dict_shapes(pc) == O.weight_shapes(od)
+    od, pc = pair("openvla-7b")
+    n_params = sum(int(np.prod(s)) for s in weights.state_dict_shapes(pc).values())
+    assert 7.5e9 < n_params < 7.7e9
+
+
+def test_synthetic_processor_and_prompt():
+    from openvla_probe_b200 import config
+    from openvla_probe_b200.openvla_utils import SyntheticProcessor, build_prompt, pool_tokens
+
+    assert build_prompt("openvla", "Pick Up The Cup") == "In: What action should the robot take to pick up the cup?\nOut:"
+    assert build_prompt("openvla-v01-7b", "x").endswith("ASSISTANT:")
+    p = SyntheticProcessor(config.tiny(), prompt_len=11)
+    out = p("hello", np.zeros((56, 56, 3), np.uint8))
+    assert out["input_ids"].shape == (1, 11) and out["input_ids"][0, 0] == 1
+    assert out["pixel_values"].shape == (1, 6, 56, 56)
+    assert torch.allclose(out["pixel_values"][0, 3:], torch.full((3, 56, 56), -1.0))
+    with pytest.raises(AssertionError):
+        pool_tokens(torch.zeros(2, 3, 4))
+    assert pool_tokens(torch.ones(1, 3, 4), "final").shape == (4,)
