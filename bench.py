@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bs1", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--lite", action="store_true",
+                    help="profiling mode for ncu: exactly --warmup untimed steps, no e2e / bs1 / CPU legs")
     return ap.parse_args()
 
 
@@ -259,7 +261,8 @@ def main():
     def step_device():
         return model.engine.run(ids_dev, px_dev, pool_len, 0, n_act)
 
-    for _ in range(max(3, args.warmup)):
+    n_warm = args.warmup if args.lite else max(3, args.warmup)
+    for _ in range(n_warm):
         step_device()
     # ---- device-resident timing (value)
     cat_n = (C.c_longlong * 7)(); cat_ms = (C.c_double * 7)(); cat_fl = (C.c_double * 7)(); cat_by = (C.c_double * 7)()
@@ -286,12 +289,14 @@ def main():
     value = world * B / (ms_step / 1e3)
 
     # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region)
-    for _ in range(2):
+    if args.lite:
+        args.no_bs1 = args.no_cpu_baseline = True
+    for _ in range(0 if args.lite else 2):
         model.predict_action_and_capture(ids, unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)),
                                          pixel_values=px_pin)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(0 if args.lite else args.steps):
         embeds, actions = model.predict_action_and_capture(
             ids, unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)), pixel_values=px_pin)
     torch.cuda.synchronize()
@@ -299,7 +304,7 @@ def main():
     t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (float(t.item()) / args.steps / 1e3)
+    e2e_value = None if args.lite else world * B / (float(t.item()) / args.steps / 1e3)
     L, D = cfg.text_config.num_hidden_layers, cfg.text_config.hidden_size
     h2d = B * (P0 + 1) * 8 + px.numel() * 2
     d2h = (L + 1) * B * D * 4 + B * n_act * 8
@@ -349,7 +354,7 @@ def main():
     }
     step_tf = algorithmic_flops_per_action(cfg, T) * B / (ms_step * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"{args.config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, "

@@ -147,6 +147,32 @@ int ovla_run_host(OvlaEngine* e, const long long* input_ids_host, const void* pi
                   int pool_len, int pool_mode, int n_new_tokens, float* pooled_out_host, long long* tokens_out_host,
                   void* stream);
 
+/* ------------------------------------------------------------------ probe training
+ * Kernels around the two TF32 tcgen05 GEMMs (ovla_gemm, OVLA_KIND_TF32) of one probe step:
+ *   experiment_utils/train_object_probes.py:177-206 (masked, per-label pos_weight), train_spatial_probes.py:153-176
+ *   (un-masked mean), train_dual_head_final.py:147-232 (presence + truth heads).  Features X are fp32 [N, D]
+ *   resident in HBM; labels int8 in {-1, 0, 1}.                                                              */
+/* epoch shuffle: xp[i,:] = x[perm[i],:] (row-major, pitch ldp) and xpt[:,i] = x[perm[i],:] (transposed, pitch ldt) */
+int ovla_probe_gather(const float* x_dev, long long ldx, const long long* perm_dev, int n, int D, float* xp_dev,
+                      long long ldp, float* xpt_dev, long long ldt, void* stream);
+/* yp[i,k] = y[perm[i], keep[k]] for k < K; padding columns [K, Kpad) are -1 */
+int ovla_probe_gather_labels(const signed char* y_dev, long long ldy, const long long* perm_dev, const int* keep_dev,
+                             int n, int K, int Kpad, signed char* yp_dev, void* stream);
+/* BCEWithLogits loss + UN-normalised gradient, written transposed: dzt [heads*Kpad, n] (pitch ldt).
+ * kind0: 0 object (masked, vector pos_weight), 1 spatial (all valid), 2 presence (scalar pos_weight);
+ * heads = 2 adds the truth head (masked, no pos_weight) reading z[:, Kpad:2Kpad].
+ * stats[4] += {loss_h0, count_h0, loss_h1, count_h1} (caller zeroes it).                                    */
+int ovla_probe_bce_grad(const float* z_dev, long long ldz, const signed char* yp_dev, int n, int K, int Kpad,
+                        int kind0, int heads, const float* pos_weight_dev, float pos_weight_scalar, float* dzt_dev,
+                        long long ldt, float* stats_dev, void* stream);
+/* out[r] = sum_c a[r, c]  (bias gradient from dzt) */
+int ovla_probe_rowsum(const float* a_dev, long long lda, int rows, int cols, float* out_dev, void* stream);
+/* torch.optim.AdamW step on the flat [W (rows x D) | b (rows)] buffer; gradient rows of head h are divided by
+ * stats[2h+1] (the global count of that head's loss terms) on the device.                                  */
+int ovla_probe_adamw(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, long long n_w, int D,
+                     int rows_per_head, long long n_total, const float* stats_dev, float lr, float beta1, float beta2,
+                     float eps, float wd, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

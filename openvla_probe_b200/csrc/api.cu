@@ -107,4 +107,29 @@ int ovla_detokenize(const long long* ids, int n, int action_dim, int vocab_size,
                              static_cast<cudaStream_t>(stream));
 }
 
+
+int ovla_probe_gather(const float* x, long long ldx, const long long* perm, int n, int D, float* xp, long long ldp,
+                      float* xpt, long long ldt, void* stream) {
+  return probe_gather_launch(x, ldx, perm, n, D, xp, ldp, xpt, ldt, static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_gather_labels(const signed char* y, long long ldy, const long long* perm, const int* keep, int n, int K,
+                             int Kpad, signed char* yp, void* stream) {
+  return probe_gather_labels_launch(y, ldy, perm, keep, n, K, Kpad, yp, static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_bce_grad(const float* z, long long ldz, const signed char* y, int n, int K, int Kpad, int kind0,
+                        int heads, const float* pos_weight, float pos_weight_scalar, float* dzt, long long ldt,
+                        float* stats, void* stream) {
+  return probe_bce_grad_launch(z, ldz, y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar, dzt, ldt, stats,
+                               static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_rowsum(const float* a, long long lda, int rows, int cols, float* out, void* stream) {
+  return probe_rowsum_launch(a, lda, rows, cols, out, static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_adamw(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
+                     long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
+                     int step, void* stream) {
+  return probe_adamw_launch(p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, step,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

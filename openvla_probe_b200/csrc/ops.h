@@ -47,4 +47,18 @@ int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_s
                         int n_centers, const double* q01, const double* q99, const unsigned char* mask, double* out,
                         cudaStream_t st);
 
+
+// probe.cu
+int probe_gather_launch(const float* X, long long ldx, const long long* perm, int n, int D, float* Xp, long long ldp,
+                        float* XpT, long long ldt, cudaStream_t st);
+int probe_gather_labels_launch(const signed char* Y, long long ldy, const long long* perm, const int* keep, int n,
+                               int K, int Kpad, signed char* Yp, cudaStream_t st);
+int probe_bce_grad_launch(const float* Z, long long ldz, const signed char* Y, int n, int K, int Kpad, int kind0,
+                          int heads, const float* pos_weight, float pos_weight_scalar, float* dZT, long long ldt,
+                          float* stats, cudaStream_t st);
+int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float* out, cudaStream_t st);
+int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
+                       long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
+                       int step, cudaStream_t st);
+
 }  // namespace ovla

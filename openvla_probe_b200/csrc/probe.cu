@@ -1,0 +1,228 @@
+// Probe-training kernels (experiment_utils/train_object_probes.py:177-206, train_spatial_probes.py:153-176,
+// train_dual_head_final.py:147-232): everything around the two tcgen05 TF32 GEMMs of a step
+//   logits = X_b W^T + b            (gemm, kind::tf32, fp32 out)
+//   dW     = dZ^T X_b               (gemm on the transposed operands produced here)
+// i.e. epoch permutation gather (row-major + transposed copies of the resident features), fused
+// BCE-with-logits loss + gradient written transposed, bias-gradient row sums, and the AdamW update.
+// All of it is HBM-bound fp32 streaming with coalesced 128-byte rows.
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace ovla {
+
+// ------------------------------------------------------------------------------------------- epoch gather
+// Xp[i, :] = X[perm[i], :]  and  XpT[:, i] = X[perm[i], :]   (X fp32 [N, D]; XpT [D, ldt])
+// 32 x 32 tiles through shared memory so that both the row-major and the transposed store are coalesced.
+__global__ void __launch_bounds__(256) gather_transpose_kernel(const float* __restrict__ X, long long ldx,
+                                                               const long long* __restrict__ perm, int n, int D,
+                                                               float* __restrict__ Xp, long long ldp,
+                                                               float* __restrict__ XpT, long long ldt) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 row groups
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (i < n && c < D) {
+      v = X[perm[i] * ldx + c];
+      Xp[static_cast<long long>(i) * ldp + c] = v;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + tx;
+    if (c < D && i < n) XpT[static_cast<long long>(c) * ldt + i] = tile[tx][r];
+  }
+}
+
+int probe_gather_launch(const float* X, long long ldx, const long long* perm, int n, int D, float* Xp, long long ldp,
+                        float* XpT, long long ldt, cudaStream_t st) {
+  if (n <= 0) return 0;
+  dim3 grid((D + 31) / 32, (n + 31) / 32);
+  ProfScope prof(kCatOther, 0.0, 12.0 * n * D, st);
+  gather_transpose_kernel<<<grid, 256, 0, st>>>(X, ldx, perm, n, D, Xp, ldp, XpT, ldt);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Yp[i, k] = Y[perm[i], keep[k]] for k < K, and -1 (ignored) in the padding columns [K, Kpad)
+__global__ void gather_labels_kernel(const signed char* __restrict__ Y, long long ldy,
+                                     const long long* __restrict__ perm, const int* __restrict__ keep, int n, int K,
+                                     int Kpad, signed char* __restrict__ Yp) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * Kpad) return;
+  const int k = static_cast<int>(idx % Kpad);
+  const long long i = idx / Kpad;
+  Yp[idx] = (k < K) ? Y[perm[i] * ldy + keep[k]] : static_cast<signed char>(-1);
+}
+
+int probe_gather_labels_launch(const signed char* Y, long long ldy, const long long* perm, const int* keep, int n,
+                               int K, int Kpad, signed char* Yp, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * Kpad;
+  if (total <= 0) return 0;
+  gather_labels_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(Y, ldy, perm, keep, n, K, Kpad, Yp);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- BCE loss + gradient
+// torch.nn.BCEWithLogitsLoss(pos_weight) element:  l = (1-t) z + lw * softplus(-z),  lw = 1 + (pw-1) t
+//                                      gradient:  dl/dz = (1-t) - lw * (1 - sigmoid(z)) = sigmoid(z) lw - pw t
+// head 0 (rows [0, Kpad) of dZT) -- kind:
+//   0 "object" : target = (y==1), valid = (y!=-1), vector pos_weight, normaliser = sum(valid)      (train_object_probes.py:184-188)
+//   1 "spatial": target = y (0/1), every real column valid, vector pos_weight, normaliser = B*K     (train_spatial_probes.py:153-163)
+//   2 "presence": target = (y!=-1), every real column valid, scalar pos_weight, normaliser = B*K    (train_dual_head_final.py:158,180)
+// head 1 (rows [Kpad, 2 Kpad), dual-head only) -- "truth": target = (y==1), valid = (y!=-1), no pos_weight,
+//   normaliser = sum(valid)                                                                            (train_dual_head_final.py:183-186)
+// Gradients are written UN-normalised (the normalisers are global sums that an allreduce completes); stats gets
+// [loss_h0, count_h0, loss_h1, count_h1] accumulated with one atomic per CTA.
+__global__ void __launch_bounds__(256) bce_grad_kernel(const float* __restrict__ Z, long long ldz,
+                                                       const signed char* __restrict__ Y, int n, int K, int Kpad,
+                                                       int kind0, int heads, const float* __restrict__ pos_weight,
+                                                       float pos_weight_scalar, float* __restrict__ dZT, long long ldt,
+                                                       float* __restrict__ stats) {
+  __shared__ float tile[2][32][33];
+  __shared__ float red[4][8];
+  const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, k = k0 + tx;
+    float g0 = 0.f, g1 = 0.f;
+    if (i < n && k < K) {
+      const int y = Y[static_cast<long long>(i) * Kpad + k];
+      {
+        const float z = Z[static_cast<long long>(i) * ldz + k];
+        float t, valid, pw;
+        if (kind0 == 0) { t = (y == 1); valid = (y != -1); pw = pos_weight[k]; }
+        else if (kind0 == 1) { t = static_cast<float>(y); valid = 1.f; pw = pos_weight[k]; }
+        else { t = (y != -1); valid = 1.f; pw = pos_weight_scalar; }
+        const float lw = 1.f + (pw - 1.f) * t;
+        const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);  // softplus(-z), as torch computes it
+        const float sig = 1.f / (1.f + expf(-z));
+        acc[0] += valid * ((1.f - t) * z + lw * sp);
+        acc[1] += valid;
+        g0 = valid * (sig * lw - pw * t);
+      }
+      if (heads == 2) {
+        const float z = Z[static_cast<long long>(i) * ldz + Kpad + k];
+        const float t = (y == 1), valid = (y != -1);
+        const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);
+        const float sig = 1.f / (1.f + expf(-z));
+        acc[2] += valid * ((1.f - t) * z + sp);
+        acc[3] += valid;
+        g1 = valid * (sig - t);
+      }
+    }
+    tile[0][r][tx] = g0;
+    tile[1][r][tx] = g1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, i = i0 + tx;
+    if (k < Kpad && i < n) {  // padding label rows get zero gradients
+      dZT[static_cast<long long>(k) * ldt + i] = tile[0][tx][r];
+      if (heads == 2) dZT[static_cast<long long>(Kpad + k) * ldt + i] = tile[1][tx][r];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (tx == 0) red[j][ty] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s != 0.f) atomicAdd(stats + threadIdx.x, s);
+  }
+}
+
+int probe_bce_grad_launch(const float* Z, long long ldz, const signed char* Y, int n, int K, int Kpad, int kind0,
+                          int heads, const float* pos_weight, float pos_weight_scalar, float* dZT, long long ldt,
+                          float* stats, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (heads != 1 && heads != 2) return set_error("probe: heads must be 1 or 2");
+  if (kind0 < 0 || kind0 > 2) return set_error("probe: unknown loss kind %d", kind0);
+  if (kind0 != 2 && !pos_weight) return set_error("probe: vector pos_weight required");
+  dim3 grid((Kpad + 31) / 32, (n + 31) / 32);
+  ProfScope prof(kCatOther, 0.0, (8.0 * heads + 1.0) * n * Kpad, st);
+  bce_grad_kernel<<<grid, 256, 0, st>>>(Z, ldz, Y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar, dZT, ldt,
+                                        stats);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// db[r] = sum_i dZT[r, i]  (one warp per row)
+__global__ void rowsum_kernel(const float* __restrict__ A, long long lda, int rows, int cols, float* __restrict__ out) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += A[static_cast<long long>(r) * lda + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = s;
+}
+
+int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float* out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  rowsum_kernel<<<(rows + 7) / 8, 256, 0, st>>>(A, lda, rows, cols, out);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- AdamW
+// torch.optim.AdamW (decoupled weight decay), one thread per parameter.  params = [W (rows x D) | b (rows)] in one
+// flat buffer, grads likewise (un-normalised); row r of head h is divided by stats[2h+1], the global number of
+// loss terms of that head -- read from device memory, so no host sync separates loss and update.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n_w, int D, int rows_per_head, long long n_total,
+                             const float* __restrict__ stats, float lr, float beta1, float beta2, float eps, float wd,
+                             float bc1, float bc2_sqrt) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  const long long row = (i < n_w) ? i / D : i - n_w;
+  const int head = static_cast<int>(row / rows_per_head);
+  const float denom = stats[2 * head + 1];  // global count of the head's loss terms (after the allreduce)
+  const float grad = denom > 0.f ? g[i] / denom : 0.f;
+  float pi = p[i] * (1.f - lr * wd);
+  const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+  const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  p[i] = pi;
+}
+
+int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
+                       long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
+                       int step, cudaStream_t st) {
+  if (n_total <= 0) return 0;
+  if (step < 1) return set_error("adamw: step must be >= 1");
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  ProfScope prof(kCatOther, 0.0, 28.0 * n_total, st);
+  adamw_kernel<<<static_cast<unsigned>((n_total + 255) / 256), 256, 0, st>>>(p, g, m, v, n_w, D, rows_per_head, n_total,
+                                                                             stats, lr, beta1, beta2, eps, wd, bc1,
+                                                                             static_cast<float>(sqrt(bc2)));
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace ovla

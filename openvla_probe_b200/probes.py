@@ -1,0 +1,499 @@
+"""Probe training on the captured 4096-d layer features -- B200-native counterpart of the reference's
+`experiment_utils/train_object_probes.py`, `train_spatial_probes.py` and `train_dual_head_final.py`.
+
+Same data contract (`episode_*.pt` dicts), same split / label filtering / pos_weight rules, same
+loss definitions, AdamW hyper-parameters and output files (`linear_probe_L{L:02d}.pth`, `*_dual_head_final_L{L:02d}.pth`,
+CSV).  What changes is the execution: the whole layer dataset stays resident in HBM (fp32 [N, D] + a per-epoch
+shuffled row-major / transposed copy), and one optimisation step is five kernels behind the C ABI:
+
+    logits = X_b W^T + b        tcgen05 TF32 GEMM (fp32 accumulate)          ovla_gemm(kind=TF32)
+    dZ^T, loss, counts          fused BCE-with-logits gradient, transposed    ovla_probe_bce_grad
+    db                          row sums of dZ^T                              ovla_probe_rowsum
+    dW = dZ^T X_b               tcgen05 TF32 GEMM on the transposed copies    ovla_gemm(kind=TF32)
+    AdamW                       fused update, normalisers read on device      ovla_probe_adamw
+
+Precision: the reference runs true-fp32 matmuls (torch default allow_tf32=False); here the two GEMMs multiply in TF32
+(10-bit mantissa) with fp32 accumulation -- tests/test_gpu_probes.py states and checks the tolerance (rel-L2 <= 2e-3 on
+logits / dW per step against fp32 autograd).
+
+Multi-GPU (`torch.distributed`, NCCL over NVLink): every global batch is split evenly over the ranks; gradients are
+kept UN-normalised, so ONE allreduce(sum) of the flat [dW | db | loss, count] buffer per step yields the global
+gradient and the global `mask.sum()` normaliser together; every rank then applies the identical AdamW update.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import ctypes as C
+import glob
+import os
+import random
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+KIND_OBJECT, KIND_SPATIAL, KIND_DUAL = "object", "spatial", "dual"
+_KIND0 = {KIND_OBJECT: 0, KIND_SPATIAL: 1, KIND_DUAL: 2}
+
+
+# ----------------------------------------------------------------------------------------------- episode files
+class EpisodeWriter:
+    """Accumulates one episode exactly as run_libero_eval_object.py:254-256,309-312,357-366 does and writes
+    `episode_{n}.pt` = {"visual_semantic_encoding": {L: float32 [T, D]}, "symbolic_state_object_relations": int8
+    [T, n_rel], "symbolic_state_action_subgoals": int8 [T, n_act]} (dict keys are Python ints)."""
+
+    def __init__(self, layers: Sequence[int] = tuple(range(33))):
+        self.layers = list(layers)
+        self.embeds: Dict[int, List[np.ndarray]] = {L: [] for L in self.layers}
+        self.rel: List[np.ndarray] = []
+        self.act: List[np.ndarray] = []
+
+    def append(self, embeds: Dict[int, np.ndarray], rel_vec: np.ndarray, act_vec: np.ndarray) -> None:
+        assert set(embeds) == set(self.layers)                          # run_libero_eval_object.py:292
+        for L in self.layers:
+            self.embeds[L].append(np.asarray(embeds[L], dtype=np.float32))
+        rel_vec, act_vec = np.asarray(rel_vec, dtype=np.int8), np.asarray(act_vec, dtype=np.int8)
+        assert set(np.unique(rel_vec)).issubset({-1, 0, 1}) and set(np.unique(act_vec)).issubset({-1, 0, 1})
+        self.rel.append(rel_vec)
+        self.act.append(act_vec)
+
+    def append_batch(self, pooled: np.ndarray, rel: np.ndarray, act: np.ndarray) -> None:
+        """pooled fp32 [n_layers, B, D] straight from the engine; rel/act int8 [B, *]."""
+        for b in range(pooled.shape[1]):
+            self.append({L: pooled[L, b] for L in self.layers}, rel[b], act[b])
+
+    def save(self, path: str) -> None:
+        d = {
+            "visual_semantic_encoding": {L: torch.from_numpy(np.stack(v)) for L, v in self.embeds.items()},
+            "symbolic_state_object_relations": torch.from_numpy(np.stack(self.rel)),
+            "symbolic_state_action_subgoals": torch.from_numpy(np.stack(self.act)),
+        }
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        torch.save(d, path)
+
+
+def load_episodes(log_dir: str, exclude: Sequence[int] = ()) -> Dict[int, dict]:
+    """train_object_probes.py:59-69."""
+    files = sorted(glob.glob(os.path.join(log_dir, "episode_*.pt")))
+    files = [fp for fp in files if int(Path(fp).stem.split("_")[1]) not in set(exclude)]
+    if not files:
+        raise FileNotFoundError("No episode_*.pt after applying exclusions")
+    return {i: torch.load(fp, map_location="cpu", weights_only=False) for i, fp in enumerate(files)}
+
+
+def parse_exclusions(spec: str) -> set:
+    """train_object_probes.py:35-45."""
+    out = set()
+    if spec.strip():
+        for tok in spec.split(","):
+            tok = tok.strip()
+            if "-" in tok:
+                a, b = map(int, tok.split("-"))
+                out.update(range(a, b + 1))
+            else:
+                out.add(int(tok))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- dataset prep (host)
+@dataclass
+class ProbeSplit:
+    train_ids: List[int]
+    val_ids: List[int]
+    keep: torch.Tensor            # kept label columns (int64)
+    pos_weight: torch.Tensor      # vector [K] (object / spatial) or scalar tensor (dual)
+    num_labels: int
+
+
+def _stack_labels(cache, ids) -> torch.Tensor:
+    return torch.cat([torch.cat([cache[i]["symbolic_state_object_relations"],
+                                 cache[i]["symbolic_state_action_subgoals"]], 1) for i in ids], 0)
+
+
+def split_episodes(cache: Dict[int, dict], seed: int = 0) -> Tuple[List[int], List[int]]:
+    """Episode-level 90/10 split with random.Random(seed).shuffle (train_object_probes.py:50,72-75)."""
+    rng = random.Random(seed)
+    ep_ids = list(cache.keys())
+    rng.shuffle(ep_ids)
+    val_len = max(1, int(0.10 * len(ep_ids)))
+    return ep_ids[val_len:], ep_ids[:val_len]
+
+
+def prepare_object(cache: Dict[int, dict]) -> ProbeSplit:
+    """train_object_probes.py:72-102: keep = labels that take both 0 and 1 somewhere (train U val);
+    pos_weight = clamp((neg+1)/(pos+1), max=20) on the TRAIN split."""
+    train_ids, val_ids = split_episodes(cache)
+    Y_full = _stack_labels(cache, train_ids + val_ids)
+    mask_full = Y_full != -1
+    keep = (((Y_full == 1) & mask_full).any(0) & ((Y_full == 0) & mask_full).any(0)).nonzero(as_tuple=True)[0]
+    if len(keep) == 0:
+        raise RuntimeError("No label flips value across remaining episodes.")
+    Y_tr = _stack_labels(cache, train_ids)
+    m = Y_tr != -1
+    pos = ((Y_tr == 1) & m).sum(0).float()
+    neg = ((Y_tr == 0) & m).sum(0).float()
+    pw = ((neg + 1.0) / (pos + 1.0))[keep].clamp(max=20)
+    return ProbeSplit(train_ids, val_ids, keep, pw, Y_full.shape[1])
+
+
+def prepare_spatial(cache: Dict[int, dict]) -> ProbeSplit:
+    """train_spatial_probes.py:100-131: labels are {0,1}; keep = columns with both values in the TRAIN split;
+    pos_weight = clamp(neg/pos, max=20) with pos_cnt = Y_train.sum(0) (Appendix B pitfall kept)."""
+    train_ids, val_ids = split_episodes(cache)
+    Y_tr = _stack_labels(cache, train_ids).float()
+    pos = Y_tr.sum(0)
+    neg = Y_tr.shape[0] - pos
+    keep = ((pos > 0) & (neg > 0)).nonzero(as_tuple=True)[0]
+    if len(keep) == 0:
+        raise RuntimeError("No label flips value across the training episodes.")
+    pw = (neg[keep] / pos[keep].clamp(min=1.0)).clamp(max=20)
+    return ProbeSplit(train_ids, val_ids, keep, pw, Y_tr.shape[1])
+
+
+def prepare_dual(cache: Dict[int, dict], seed: int = 0) -> ProbeSplit:
+    """train_dual_head_final.py:100-127: keep labels whose TRAIN 0/1 frequency is in (1 %, 99 %);
+    presence pos_weight = #absent / (#present + 1e-9) over the kept training labels (a scalar)."""
+    train_ids, val_ids = split_episodes(cache, seed)
+    Y_tr = _stack_labels(cache, train_ids)
+    m = Y_tr != -1
+    cnt = m.sum(0)
+    freq = torch.full((Y_tr.shape[1],), -1.0)
+    ok = cnt > 0
+    freq[ok] = ((Y_tr == 1) & m).sum(0)[ok].float() / cnt[ok]
+    keep = ((freq > 0.01) & (freq < 0.99)).nonzero(as_tuple=True)[0]
+    if len(keep) == 0:
+        keep = torch.arange(Y_tr.shape[1])
+    present = (Y_tr[:, keep] != -1)
+    n_present = int(present.sum())
+    pw = torch.tensor((present.numel() - n_present) / (n_present + 1e-9))
+    return ProbeSplit(train_ids, val_ids, keep, pw, Y_tr.shape[1])
+
+
+def layer_matrix(cache: Dict[int, dict], ids: Sequence[int], layer: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The samples StepDS enumerates (train_object_probes.py:129-145), as dense tensors: X fp32 [N, D], Y int8 [N, L]."""
+    xs, ys = [], []
+    for i in ids:
+        enc = cache[i]["visual_semantic_encoding"]
+        if layer not in enc:
+            continue
+        x = enc[layer].float()
+        y = torch.cat([cache[i]["symbolic_state_object_relations"], cache[i]["symbolic_state_action_subgoals"]], 1)
+        n = min(x.shape[0], y.shape[0])
+        xs.append(x[:n])
+        ys.append(y[:n].to(torch.int8))
+    if not xs:
+        return torch.empty(0, 0), torch.empty(0, 0, dtype=torch.int8)
+    return torch.cat(xs), torch.cat(ys)
+
+
+# ----------------------------------------------------------------------------------------------- sharding (host logic)
+def shard_batches(n: int, batch: int, world: int, rank: int, drop_last: bool) -> List[Tuple[int, int]]:
+    """Row ranges [lo, hi) of the shuffled order that `rank` processes, one per optimisation step: every global
+    batch [s*batch, min((s+1)*batch, n)) is cut into `world` near-equal contiguous pieces (sizes differ by <= 1)."""
+    out = []
+    n_steps = n // batch if drop_last else (n + batch - 1) // batch
+    for s in range(n_steps):
+        lo, hi = s * batch, min((s + 1) * batch, n)
+        m = hi - lo
+        base, extra = divmod(m, world)
+        a = lo + rank * base + min(rank, extra)
+        b = a + base + (1 if rank < extra else 0)
+        out.append((a, b))
+    return out
+
+
+def allreduce_flat(buf: torch.Tensor, group=None) -> None:
+    """One collective per step: [dW | db | loss_h0, count_h0, loss_h1, count_h1] summed over ranks."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+
+
+def adamw_reference_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, wd=1e-4):
+    """torch.optim.AdamW update rule in plain tensor ops (host-side twin of ovla_probe_adamw, used by CPU tests)."""
+    p.mul_(1 - lr * wd)
+    m.lerp_(g, 1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
+
+
+# ----------------------------------------------------------------------------------------------- device trainer
+class ProbeTrainer:
+    """One probe (object / spatial: a single nn.Linear(D, K); dual: presence + truth heads) trained on one layer."""
+
+    def __init__(self, kind: str, D: int, K: int, pos_weight: torch.Tensor, batch: int = 4096, lr: float = 1e-3,
+                 weight_decay: float = 1e-4, device: int = 0, group=None, init_state: Optional[Dict[str, torch.Tensor]] = None):
+        from . import _lib
+
+        self._lib_mod = _lib
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.OvlaError("probe training needs a CUDA device (sm_100a); there is no CPU fallback")
+        if D % 4:
+            raise ValueError("feature dim must be a multiple of 4")
+        self.kind, self.D, self.K = kind, D, K
+        self.heads = 2 if kind == KIND_DUAL else 1
+        self.Kpad = (K + 7) // 8 * 8
+        self.rows = self.heads * self.Kpad
+        self.batch, self.lr, self.wd = batch, lr, weight_decay
+        self.dev = torch.device("cuda", device)
+        self.group = group
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        n_w = self.rows * D
+        self.n_w, self.n_total = n_w, n_w + self.rows
+        self.P = torch.zeros(self.n_total, dtype=torch.float32, device=self.dev)
+        self.G = torch.zeros(self.n_total + 4, dtype=torch.float32, device=self.dev)     # [dW | db | stats(4)]
+        self.M = torch.zeros_like(self.P)
+        self.V = torch.zeros_like(self.P)
+        self.step_count = 0
+        if kind == KIND_DUAL:
+            self.pw_vec, self.pw_scalar = None, float(pos_weight)
+        else:
+            pw = torch.ones(self.Kpad, dtype=torch.float32)
+            pw[:K] = pos_weight.float()
+            self.pw_vec, self.pw_scalar = pw.to(self.dev), 1.0
+        self._init_params(init_state)
+        self.last_loss = None
+
+    # -- parameters ---------------------------------------------------------------------------------
+    def _init_params(self, init_state):
+        """nn.Linear default init (kaiming-uniform a=sqrt(5)), drawn with torch on the host exactly as the reference's
+        `nn.Linear(4096, K)` would (train_object_probes.py:219), or a given state dict."""
+        W = self.P[: self.n_w].view(self.rows, self.D)
+        b = self.P[self.n_w:]
+        names = ["presence_head", "truth_head"] if self.heads == 2 else [None]
+        for h, nm in enumerate(names):
+            if init_state is None:
+                lin = torch.nn.Linear(self.D, self.K)
+                w0, b0 = lin.weight.detach(), lin.bias.detach()
+            else:
+                pre = f"{nm}." if nm else ""
+                w0, b0 = init_state[pre + "weight"].float(), init_state[pre + "bias"].float()
+            W[h * self.Kpad: h * self.Kpad + self.K].copy_(w0)
+            b[h * self.Kpad: h * self.Kpad + self.K].copy_(b0)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        W = self.P[: self.n_w].view(self.rows, self.D)
+        b = self.P[self.n_w:]
+        if self.heads == 1:
+            return {"weight": W[: self.K].cpu().clone(), "bias": b[: self.K].cpu().clone()}
+        return {"presence_head.weight": W[: self.K].cpu().clone(), "presence_head.bias": b[: self.K].cpu().clone(),
+                "truth_head.weight": W[self.Kpad: self.Kpad + self.K].cpu().clone(),
+                "truth_head.bias": b[self.Kpad: self.Kpad + self.K].cpu().clone()}
+
+    # -- native calls --------------------------------------------------------------------------------
+    def _gemm_tf32(self, A, lda, Wt, ldw, M, N, K, out, ldo, bias=None):
+        epi = self._lib_mod.GemmEpilogue()
+        if bias is not None:
+            epi.bias_f32 = bias.data_ptr()
+        self._lib_mod.check(self.lib.ovla_gemm(C.c_void_p(A), C.c_longlong(lda), C.c_void_p(Wt), C.c_longlong(ldw),
+                                               M, N, K, 2, 1, C.c_void_p(out), C.c_longlong(ldo), C.byref(epi), 0, 0,
+                                               self._lib_mod.stream_ptr()))
+
+    def logits(self, X: torch.Tensor) -> torch.Tensor:
+        """X fp32 [n, D] on the device -> logits fp32 [n, heads*Kpad]."""
+        n = X.shape[0]
+        Z = torch.empty(n, self.rows, dtype=torch.float32, device=self.dev)
+        if n:
+            self._gemm_tf32(X.data_ptr(), self.D, self.P.data_ptr(), self.D, n, self.rows, self.D, Z.data_ptr(), self.rows,
+                            bias=self.P[self.n_w:])
+        return Z
+
+    def load_epoch(self, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, perm: torch.Tensor, drop_last: bool):
+        """Gather this rank's rows of the shuffled epoch into contiguous row-major + transposed copies."""
+        n = X.shape[0]
+        ranges = shard_batches(n, self.batch, self.world, self.rank, drop_last)
+        idx = torch.cat([perm[a:b] for a, b in ranges]) if ranges else perm[:0]
+        n_loc = idx.numel()
+        ldt = (n_loc + 3) // 4 * 4
+        self.Xp = torch.empty(max(n_loc, 1), self.D, dtype=torch.float32, device=self.dev)
+        self.XpT = torch.zeros(self.D, max(ldt, 4), dtype=torch.float32, device=self.dev)
+        self.Yp = torch.empty(max(n_loc, 1), self.Kpad, dtype=torch.int8, device=self.dev)
+        idx_d = idx.to(self.dev, torch.int64)
+        keep_d = keep.to(self.dev, torch.int32)
+        st = self._lib_mod.stream_ptr()
+        ck = self._lib_mod.check
+        if n_loc:
+            ck(self.lib.ovla_probe_gather(C.c_void_p(X.data_ptr()), C.c_longlong(X.stride(0)), C.c_void_p(idx_d.data_ptr()),
+                                          n_loc, self.D, C.c_void_p(self.Xp.data_ptr()), C.c_longlong(self.D),
+                                          C.c_void_p(self.XpT.data_ptr()), C.c_longlong(self.XpT.stride(0)), st))
+            ck(self.lib.ovla_probe_gather_labels(C.c_void_p(Y.data_ptr()), C.c_longlong(Y.stride(0)),
+                                                 C.c_void_p(idx_d.data_ptr()), C.c_void_p(keep_d.data_ptr()), n_loc,
+                                                 self.K, self.Kpad, C.c_void_p(self.Yp.data_ptr()), st))
+        # local [lo, hi) of every step inside the gathered copy
+        self.steps, off = [], 0
+        for a, b in ranges:
+            self.steps.append((off, off + (b - a)))
+            off += b - a
+        bmax = max([hi - lo for lo, hi in self.steps], default=0)
+        self.ldz_t = max((bmax + 3) // 4 * 4, 4)
+        self.Z = torch.empty(max(bmax, 1), self.rows, dtype=torch.float32, device=self.dev)
+        self.dZT = torch.zeros(self.rows, self.ldz_t, dtype=torch.float32, device=self.dev)
+
+    def train_step(self, s: int) -> None:
+        """One optimisation step on local rows self.steps[s] (all ranks call this in lock-step)."""
+        lo, hi = self.steps[s]
+        n = hi - lo
+        st = self._lib_mod.stream_ptr()
+        ck = self._lib_mod.check
+        self.G.zero_()
+        stats = self.G[self.n_total:]
+        if n > 0:
+            xp = self.Xp.data_ptr() + lo * self.D * 4
+            self._gemm_tf32(xp, self.D, self.P.data_ptr(), self.D, n, self.rows, self.D, self.Z.data_ptr(), self.rows,
+                            bias=self.P[self.n_w:])
+            ck(self.lib.ovla_probe_bce_grad(C.c_void_p(self.Z.data_ptr()), C.c_longlong(self.rows),
+                                            C.c_void_p(self.Yp.data_ptr() + lo * self.Kpad), n, self.K, self.Kpad,
+                                            _KIND0[self.kind], self.heads,
+                                            C.c_void_p(self.pw_vec.data_ptr()) if self.pw_vec is not None else None,
+                                            C.c_float(self.pw_scalar), C.c_void_p(self.dZT.data_ptr()),
+                                            C.c_longlong(self.ldz_t), C.c_void_p(stats.data_ptr()), st))
+            ck(self.lib.ovla_probe_rowsum(C.c_void_p(self.dZT.data_ptr()), C.c_longlong(self.ldz_t), self.rows, n,
+                                          C.c_void_p(self.G.data_ptr() + self.n_w * 4), st))
+            # dW[rows, D] = dZT[rows, n] . (XpT[:, lo:hi])^T      (contraction over the local batch)
+            self._gemm_tf32(self.dZT.data_ptr(), self.ldz_t, self.XpT.data_ptr() + lo * 4, self.XpT.stride(0),
+                            self.rows, self.D, n, self.G.data_ptr(), self.D)
+        allreduce_flat(self.G, self.group)
+        self.step_count += 1
+        ck(self.lib.ovla_probe_adamw(C.c_void_p(self.P.data_ptr()), C.c_void_p(self.G.data_ptr()),
+                                     C.c_void_p(self.M.data_ptr()), C.c_void_p(self.V.data_ptr()),
+                                     C.c_longlong(self.n_w), self.D, self.Kpad, C.c_longlong(self.n_total),
+                                     C.c_void_p(stats.data_ptr()), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999),
+                                     C.c_float(1e-8), C.c_float(self.wd), self.step_count, st))
+
+    def step_loss(self) -> float:
+        """Loss of the last step (host sync): loss_h0/count_h0 (+ loss_h1/count_h1)."""
+        s = self.G[self.n_total:].cpu()
+        loss = float(s[0] / s[1]) if s[1] > 0 else 0.0
+        if self.heads == 2 and s[3] > 0:
+            loss += float(s[2] / s[3])
+        return loss
+
+    def fit(self, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, epochs: int, seed: int = 0,
+            drop_last: bool = False, on_epoch: Optional[Callable[[int], None]] = None) -> None:
+        """X fp32 [N, D], Y int8 [N, n_labels] (host or device); shuffles every epoch like DataLoader(shuffle=True)."""
+        X = X.to(self.dev, torch.float32).contiguous()
+        Y = Y.to(self.dev, torch.int8).contiguous()
+        g = torch.Generator().manual_seed(seed)
+        for e in range(epochs):
+            perm = torch.randperm(X.shape[0], generator=g)
+            self.load_epoch(X, Y, keep, perm, drop_last)
+            for s in range(len(self.steps)):
+                self.train_step(s)
+            if on_epoch:
+                on_epoch(e)
+
+
+# ----------------------------------------------------------------------------------------------- evaluation (host, as reference)
+def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, thresh: float = 0.5):
+    """Validation metrics exactly as the reference computes them on the host with sklearn
+    (train_object_probes.py:190-206; train_dual_head_final.py:196-232); logits come from the device GEMM."""
+    from sklearn.metrics import average_precision_score, f1_score
+
+    Z = trainer.logits(X.to(trainer.dev, torch.float32).contiguous()).cpu()
+    y = Y[:, keep].long().cpu()
+    K, Kp = trainer.K, trainer.Kpad
+    if kind == KIND_DUAL:
+        pres_t, truth_t, mask = (y != -1).long(), (y == 1).long(), (y != -1)
+        pres_p = (Z[:, :K].sigmoid() > 0.5).long()
+        truth_p = (Z[:, Kp:Kp + K].sigmoid() > 0.5).long()
+        pres_acc = float((pres_p == pres_t).float().mean()) if y.numel() else 0.0
+        truth_acc = float((truth_p == truth_t)[mask].float().mean()) if mask.any() else 0.0
+        pres_f1 = f1_score(pres_t.view(-1).numpy(), pres_p.view(-1).numpy(), average="binary", pos_label=1, zero_division=0)
+        truth_f1 = f1_score(truth_t[mask].numpy(), truth_p[mask].numpy(), labels=[0, 1], average="macro",
+                            zero_division=0) if mask.any() else 0.0
+        return dict(pres_acc_va=pres_acc, truth_acc_va=truth_acc, pres_f1_va=pres_f1, truth_f1_va=truth_f1)
+    probs = Z[:, :K].sigmoid()
+    if kind == KIND_OBJECT:
+        mask, target = (y != -1), (y == 1).float()
+    else:
+        mask, target = torch.ones_like(y, dtype=torch.bool), y.float()
+    if not mask.any():
+        return dict(val_acc=0.0, val_f1=0.0, val_ap=0.0)
+    pred = (probs > thresh).long()
+    acc = float((pred[mask] == target[mask]).float().mean())
+    f1 = f1_score(target[mask].numpy(), pred[mask].numpy(), average="macro", zero_division=0)
+    ap = average_precision_score(target[mask].numpy(), probs[mask].numpy(), average="macro")
+    return dict(val_acc=acc, val_f1=f1, val_ap=ap)
+
+
+# ----------------------------------------------------------------------------------------------- per-layer driver
+def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 20, batch: int = 4096, device: int = 0,
+                 out_dir: str = ".", exclude: Sequence[int] = (), seed: int = 0, group=None, verbose: bool = True):
+    """Per-layer loop of the three reference scripts (train_object_probes.py:208-232, train_spatial_probes.py:179-204,
+    train_dual_head_final.py:236-290).  Rank 0 writes the `.pth` files and the CSV."""
+    import pandas as pd
+
+    cache = load_episodes(log_dir, exclude)
+    split = {KIND_OBJECT: prepare_object, KIND_SPATIAL: prepare_spatial, KIND_DUAL: prepare_dual}[kind](cache)
+    if kind == KIND_DUAL:
+        torch.manual_seed(seed)
+    records = []
+    rank0 = True
+    for L in layers:
+        Xtr, Ytr = layer_matrix(cache, split.train_ids, L)
+        Xva, Yva = layer_matrix(cache, split.val_ids, L)
+        if Xtr.shape[0] == 0 or Xva.shape[0] == 0:
+            records.append(dict(layer=L, status="skipped_empty_data"))
+            continue
+        tr = ProbeTrainer(kind, Xtr.shape[1], len(split.keep), split.pos_weight, batch=batch, device=device, group=group)
+        rank0 = tr.rank == 0
+        tr.fit(Xtr, Ytr, split.keep, epochs, seed=seed + L, drop_last=(kind == KIND_DUAL))
+        rec = dict(layer=L, **evaluate(kind, tr, Xva, Yva, split.keep))
+        records.append(rec)
+        if rank0:
+            os.makedirs(out_dir, exist_ok=True)
+            if kind == KIND_DUAL:
+                torch.save({"model_type": "DualHeadProbe", "state_dict": tr.state_dict(), "layer": L,
+                            "kept_indices": split.keep.tolist(), "input_dim": tr.D, "num_output_labels": tr.K,
+                            "presence_pos_weight_used": float(split.pos_weight)},
+                           os.path.join(out_dir, f"linear_probe_dual_head_final_L{L:02d}.pth"))
+            else:
+                torch.save({"state_dict": tr.state_dict(), "layer": L, "kept": split.keep.tolist()},
+                           os.path.join(out_dir, f"linear_probe_L{L:02d}.pth"))
+            if verbose:
+                print(f"L{L:02d}  " + "  ".join(f"{k}={v:.3f}" for k, v in rec.items() if k != "layer"))
+    if rank0:
+        name = {KIND_OBJECT: "probe_metrics_object.csv", KIND_SPATIAL: "probe_metrics_spatial.csv",
+                KIND_DUAL: "probe_metrics_dual_head_final.csv"}[kind]
+        pd.DataFrame(records).to_csv(os.path.join(out_dir, name), index=False)
+    return records
+
+
+def main():
+    cli = argparse.ArgumentParser(description="B200-native probe training (object / spatial / dual-head)")
+    cli.add_argument("--kind", default=KIND_OBJECT, choices=[KIND_OBJECT, KIND_SPATIAL, KIND_DUAL])
+    cli.add_argument("--log_dir", default="experiments/logs", help="folder containing episode_*.pt")
+    cli.add_argument("--epochs", type=int, default=20)
+    cli.add_argument("--batch", type=int, default=4096)
+    cli.add_argument("--layers", default="all", help="comma-sep list, e.g. 32 or 0,8,16,32; 'all' = 0-32")
+    cli.add_argument("--exclude_eps", default="")
+    cli.add_argument("--out_dir", default=".")
+    args = cli.parse_args()
+    layers = list(range(33)) if args.layers.strip().lower() == "all" else [int(x) for x in args.layers.split(",")]
+    assert all(0 <= L <= 32 for L in layers), "layer index must be 0-32"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    train_probes(args.kind, args.log_dir, layers, args.epochs, args.batch, device=local, out_dir=args.out_dir,
+                 exclude=sorted(parse_exclusions(args.exclude_eps)))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""Host logic of the multi-GPU probe step, exercised on CPU with the gloo backend (world_size 2):
+batch sharding, the single flat allreduce of [dW | db | loss, count], and the global `mask.sum()` normaliser.
+The per-rank gradient here is a plain-torch stand-in for the CUDA kernels (same un-normalised definition)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from openvla_probe_b200.probes import (adamw_reference_step, allreduce_flat, layer_matrix, prepare_dual,
+                                        prepare_object, prepare_spatial, shard_batches, split_episodes)
+
+
+def test_shard_batches_partition():
+    for n, batch, world, drop in [(1000, 256, 2, False), (1000, 256, 3, True), (7, 4, 8, False), (4096, 4096, 8, False)]:
+        per_rank = [shard_batches(n, batch, world, r, drop) for r in range(world)]
+        n_steps = n // batch if drop else -(-n // batch)
+        assert all(len(p) == n_steps for p in per_rank)
+        for s in range(n_steps):
+            lo, hi = s * batch, min((s + 1) * batch, n)
+            pieces = [per_rank[r][s] for r in range(world)]
+            assert pieces[0][0] == lo and pieces[-1][1] == hi
+            assert all(pieces[i][1] == pieces[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in pieces]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _local_unnormalised(W, b, X, Y, pw):
+    """Masked pos-weighted BCE, gradient and loss summed (not averaged) over the local rows."""
+    z = X @ W.t() + b
+    t, m = (Y == 1).float(), (Y != -1).float()
+    lw = 1 + (pw - 1) * t
+    loss = (m * ((1 - t) * z + lw * torch.nn.functional.softplus(-z))).sum()
+    g = m * (torch.sigmoid(z) * lw - pw * t)
+    return g.t() @ X, g.sum(0), loss, m.sum()
+
+
+def _worker(rank, world, port, X, Y, pw, W0, b0, perm, batch, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W, b = W0.clone(), b0.clone()
+    P = torch.cat([W.flatten(), b])
+    M, V = torch.zeros_like(P), torch.zeros_like(P)
+    steps = shard_batches(X.shape[0], batch, world, rank, False)
+    for s, (lo, hi) in enumerate(steps):
+        idx = perm[lo:hi]
+        K, D = W0.shape
+        Wc, bc = P[: K * D].view(K, D), P[K * D:]
+        dW, db, loss, cnt = _local_unnormalised(Wc, bc, X[idx], Y[idx], pw)
+        flat = torch.cat([dW.flatten(), db, torch.stack([loss, cnt])])
+        allreduce_flat(flat)
+        g = flat[:-2] / flat[-1]
+        adamw_reference_step(P, g, M, V, s + 1)
+    if rank == 0:
+        out.put(P.clone())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_step_equals_single_process_step():
+    torch.manual_seed(0)
+    N, D, K, batch = 300, 32, 11, 64
+    X = torch.randn(N, D)
+    Y = torch.randint(-1, 2, (N, K)).to(torch.int8)
+    pw = 0.5 + torch.rand(K) * 4
+    lin = torch.nn.Linear(D, K)
+    W0, b0 = lin.weight.detach().clone(), lin.bias.detach().clone()
+    perm = torch.randperm(N)
+    # single process, torch autograd + torch.optim.AdamW = the reference's step (train_object_probes.py:184-189)
+    params = [W0.clone().requires_grad_(True), b0.clone().requires_grad_(True)]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    bce = torch.nn.BCEWithLogitsLoss(reduction="none", pos_weight=pw)
+    for s in range(-(-N // batch)):
+        idx = perm[s * batch: (s + 1) * batch]
+        z = X[idx] @ params[0].t() + params[1]
+        mask = (Y[idx] != -1)
+        loss = (bce(z, (Y[idx] == 1).float()) * mask.float()).sum() / mask.sum()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    want = torch.cat([params[0].detach().flatten(), params[1].detach()])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, X, Y, pw, W0, b0, perm, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.allclose(got, want, rtol=0, atol=2e-6)
+
+
+def _fake_cache(n_eps=20, T=15, n_rel=12, n_act=4, D=8, spatial=False, seed=0):
+    rng = np.random.default_rng(seed)
+    cache = {}
+    for i in range(n_eps):
+        lab = rng.integers(0 if spatial else -1, 2, (T, n_rel + n_act)).astype(np.int8)
+        lab[:, 0] = 1            # constant column -> dropped by the keep filters
+        cache[i] = {
+            "visual_semantic_encoding": {0: torch.from_numpy(rng.normal(size=(T, D)).astype(np.float32))},
+            "symbolic_state_object_relations": torch.from_numpy(lab[:, :n_rel]),
+            "symbolic_state_action_subgoals": torch.from_numpy(lab[:, n_rel:]),
+        }
+    return cache
+
+
+def test_split_keep_and_pos_weight_rules():
+    cache = _fake_cache()
+    tr, va = split_episodes(cache)
+    assert len(va) == 2 and len(tr) == 18 and not set(tr) & set(va)
+    import random
+    ids = list(cache.keys()); random.Random(0).shuffle(ids)
+    assert va == ids[:2] and tr == ids[2:]                     # train_object_probes.py:72-75
+    sp = prepare_object(cache)
+    assert 0 not in sp.keep.tolist() and len(sp.keep) == 15 and float(sp.pos_weight.max()) <= 20
+    Y = torch.cat([torch.cat([cache[i]["symbolic_state_object_relations"], cache[i]["symbolic_state_action_subgoals"]], 1)
+                   for i in sp.train_ids])
+    k = int(sp.keep[3])
+    want = (float(((Y[:, k] == 0)).sum()) + 1) / (float((Y[:, k] == 1).sum()) + 1)
+    assert abs(float(sp.pos_weight[3]) - min(want, 20.0)) < 1e-6
+    sd = prepare_dual(cache)
+    assert sd.pos_weight.dim() == 0 and 0 not in sd.keep.tolist()
+    ss = prepare_spatial(_fake_cache(spatial=True))
+    assert 0 not in ss.keep.tolist()
+    X, Yl = layer_matrix(cache, sp.train_ids, 0)
+    assert X.shape == (18 * 15, 8) and Yl.shape == (18 * 15, 16) and Yl.dtype == torch.int8
+    assert layer_matrix(cache, sp.train_ids, 5)[0].numel() == 0  # layer absent -> empty (StepDS `layer in cache[...]`)
