@@ -91,6 +91,11 @@ int ovla_detokenize(const long long* ids_dev, int n, int action_dim, int vocab_s
 /* small-batch (M <= 8) weight-streaming GEMM with the same epilogues as ovla_gemm */
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream);
+/* one cached decode step of LlamaAttention for B single-token rows: RoPE(q,k) at `pos`, append k/v to the cache
+ * [B, H, Tmax, 128], attention over the pos+1 keys; qkv is the raw fused projection [B, 3*H*128] */
+int ovla_decode_rope_attention(const void* qkv_dev, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
+                               void* k_cache_dev, void* v_cache_dev, int B, int H, int head_dim, int Tmax,
+                               void* out_dev, long long o_ld, void* stream);
 
 /* ------------------------------------------------------------------ engine
  * Stands behind OpenVLAForActionPrediction (modeling_prismatic.py:491-562) + get_vla_action's capture

@@ -70,7 +70,8 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
 
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream) {
-  return gemv_launch(x_dev, ldx, w_dev, ldw, M, N, K, mode, to_epi(out_dev, ldo, epi), static_cast<cudaStream_t>(stream));
+  return gemv_launch(x_dev, ldx, w_dev, ldw, M, N, K, mode, to_epi(out_dev, ldo, epi),
+                     static_cast<cudaStream_t>(stream));
 }
 int ovla_layernorm(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
                    int rows, int D, void* stream) {
@@ -88,6 +89,12 @@ int ovla_flash_attention(const void* q, const void* k, const void* v, void* o, c
 int ovla_decode_attention(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
                           int Tmax, int ctx, void* out, long long o_ld, void* stream) {
   return decode_attn_launch(q, q_ld, kc, vc, B, H, head_dim, Tmax, ctx, out, o_ld, static_cast<cudaStream_t>(stream));
+}
+int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
+                               void* kc, void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
+                               void* stream) {
+  return decode_rope_attn_launch(qkv, qkv_ld, cos_dev, sin_dev, pos, kc, vc, B, H, head_dim, Tmax, out, o_ld,
+                                 static_cast<cudaStream_t>(stream));
 }
 int ovla_rope_kv(void* qkv, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
                  void* kc, void* vc, int Tmax, void* stream) {

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -52,6 +53,15 @@ struct LayerW {
 
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
+struct GraphKey {
+  OvlaRunArgs a;  // every pointer and size the captured pass depends on
+  bool operator<(const GraphKey& o) const { return memcmp(&a, &o.a, sizeof(a)) < 0; }
+};
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+
 }  // namespace
 
 struct OvlaEngine {
@@ -78,6 +88,11 @@ struct OvlaEngine {
   float *pooled = nullptr, *logits = nullptr;
   long long* tokens = nullptr;
   int* err_flag = nullptr;
+  // CUDA-graph cache for launch-bound small batches (see ovla_run)
+  int graph_max_batch = 16;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  std::map<GraphKey, GraphEntry> graphs;
   // staging for ovla_run_host
   long long* in_ids = nullptr;
   bf16* in_px = nullptr;
@@ -239,6 +254,11 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
 extern "C" void ovla_destroy(OvlaEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -462,7 +482,10 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, cudaStream_t st) {
   return 0;
 }
 
-int run_llm_layers(OvlaEngine* e, int B, int T, int pos0, const OvlaRunArgs* a, bool prefill, cudaStream_t st) {
+// Llama prefill over all B*T rows: RMSNorm -> QKV GEMM -> RoPE + KV write -> causal flash attention -> o_proj(+res)
+// -> RMSNorm -> gate/up GEMM with SwiGLU epilogue -> down(+res); the capture kernel pools the residual stream
+// (hidden_states[i], i < L) before each layer and the post-final-norm states (hidden_states[L]) at the end.
+int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t st) {
   const OvlaDims& d = e->d;
   const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim, rows = B * T;
   const int Tmax = d.max_seq;
@@ -471,25 +494,17 @@ int run_llm_layers(OvlaEngine* e, int B, int T, int pos0, const OvlaRunArgs* a, 
                              1LL * H * Tmax * hd, hd, 1LL * Tmax * hd, 1LL * D * T, D, hd};
   for (int i = 0; i < d.llm_layers; ++i) {
     LayerW& l = e->layers[i];
-    if (prefill) {
-      if (a->pool_len > 0)
-        OVLA_TRY(pool_tokens_launch(e->l_x, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
-                                    e->pooled + 1LL * i * B * D, D, st));
-      if (a->hidden_out_dev)
-        CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
-                                 sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
-    }
+    if (a->pool_len > 0)
+      OVLA_TRY(pool_tokens_launch(e->l_x, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
+                                  e->pooled + 1LL * i * B * D, D, st));
+    if (a->hidden_out_dev)
+      CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
+                               sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, rows, D, st));
     OVLA_TRY(linear(e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
-    // NB: the KV cache batch stride is max_batch-independent: caches are indexed [b][h][t] with b < B
-    OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, pos0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i),
-                            e->v_cache(i), Tmax, st));
-    if (prefill) {
-      OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
-    } else {
-      OVLA_TRY(decode_attn_launch(e->l_qkv, 3LL * D, e->k_cache(i), e->v_cache(i), B, H, hd, Tmax, pos0 + 1,
-                                  e->l_attn, D, st));
-    }
+    OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
+                            Tmax, st));
+    OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
     OVLA_TRY(linear(e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));
     OVLA_TRY(linear(e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,
@@ -498,22 +513,43 @@ int run_llm_layers(OvlaEngine* e, int B, int T, int pos0, const OvlaRunArgs* a, 
   }
   // final norm (hidden_states[L] is post-norm)
   OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, rows, D, st));
-  if (prefill) {
-    if (a->pool_len > 0)
-      OVLA_TRY(pool_tokens_launch(e->l_h, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
-                                  e->pooled + 1LL * d.llm_layers * B * D, D, st));
-    if (a->hidden_out_dev)
-      CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * d.llm_layers * rows * D, e->l_h,
-                               sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
+  if (a->pool_len > 0)
+    OVLA_TRY(pool_tokens_launch(e->l_h, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
+                                e->pooled + 1LL * d.llm_layers * B * D, D, st));
+  if (a->hidden_out_dev)
+    CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * d.llm_layers * rows * D, e->l_h,
+                             sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// One cached decode step for B single-token rows at position `pos`: 7 kernels per layer (RMSNorm, QKV, fused
+// RoPE + KV append + attention, o_proj(+res), RMSNorm, gate/up SwiGLU, down(+res)); for B <= 8 the linears are
+// weight-streaming GEMVs chained with programmatic dependent launch.  Ends with final norm + lm_head (fp32 storage of
+// bf16-rounded logits, as HF's `.float()`).
+int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t st) {
+  const OvlaDims& d = e->d;
+  const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim;
+  const int Tmax = d.max_seq;
+  for (int i = 0; i < d.llm_layers; ++i) {
+    LayerW& l = e->layers[i];
+    OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, B, D, st));
+    OVLA_TRY(linear(e->l_h, D, l.qkv_w, B, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(decode_rope_attn_launch(e->l_qkv, 3LL * D, e->rope_cos.ptr, e->rope_sin.ptr, pos, e->k_cache(i),
+                                     e->v_cache(i), B, H, hd, Tmax, e->l_attn, D, st));
+    OVLA_TRY(linear(e->l_attn, D, l.o_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, B, D, st));
+    OVLA_TRY(linear(e->l_h, D, l.gate_up_w, B, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0, 0,
+                    st));
+    OVLA_TRY(linear(e->l_act, d.llm_inter, l.down_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
   }
+  OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, B, D, st));
+  OVLA_TRY(linear(e->l_h, D, e->lm_head, B, kModeF32, logits, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
   return 0;
 }
 
 }  // namespace
 
-extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
-  if (!e || !a) return set_error("ovla_run: null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
   CUDA_TRY(cudaSetDevice(e->device));
   const OvlaDims& d = e->d;
   const int B = a->B, P = a->P, np = e->np, D = d.llm_dim;
@@ -550,30 +586,95 @@ extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
 
   // ---- splice + prefill
   OVLA_TRY(embed_splice_launch(a->input_ids_dev, B, P, e->embed.ptr, d.vocab, proj_out, np, D, e->l_x, e->err_flag, st));
-  OVLA_TRY(run_llm_layers(e, B, T, 0, a, true, st));
+  OVLA_TRY(run_prefill(e, B, T, a, st));
   if (a->pool_len > 0 && a->pooled_out_dev)
     CUDA_TRY(cudaMemcpyAsync(a->pooled_out_dev, e->pooled, sizeof(float) * (d.llm_layers + 1LL) * B * D,
                              cudaMemcpyDeviceToDevice, st));
 
-  // ---- greedy decode: lm_head on the last position only, argmax, then cached single-token steps
+  // ---- greedy decode: lm_head on the last prefill position only, argmax, then cached single-token steps
   for (int s = 0; s < n_new; ++s) {
-    const bf16* last = (s == 0) ? e->l_h + 1LL * (T - 1) * D : e->l_h;
-    const long long ld_last = (s == 0) ? 1LL * T * D : D;
     float* lg = a->step_logits_out_dev ? a->step_logits_out_dev + 1LL * s * B * d.vocab : e->logits;
-    // HF: logits = lm_head(h) in bf16, then .float()  => fp32 storage of bf16-rounded values
-    OVLA_TRY(linear(last, ld_last, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
-    OVLA_TRY(argmax_launch(lg, d.vocab, B, d.vocab, e->tokens + 1LL * s * B, st));
-    if (s + 1 < n_new) {
-      OVLA_TRY(embed_splice_launch(e->tokens + 1LL * s * B, B, 1, e->embed.ptr, d.vocab, nullptr, 0, D, e->l_x,
+    if (s == 0) {
+      // HF: logits = lm_head(h) in bf16, then .float()  => fp32 storage of bf16-rounded values
+      OVLA_TRY(linear(e->l_h + 1LL * (T - 1) * D, 1LL * T * D, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr,
+                      nullptr, 0, 0, 1, st));
+    } else {
+      OVLA_TRY(embed_splice_launch(e->tokens + 1LL * (s - 1) * B, B, 1, e->embed.ptr, d.vocab, nullptr, 0, D, e->l_x,
                                    e->err_flag, st));
-      OVLA_TRY(run_llm_layers(e, B, 1, T + s, a, false, st));
+      OVLA_TRY(run_decode_step(e, B, T + s - 1, lg, st));
     }
+    OVLA_TRY(argmax_launch(lg, d.vocab, B, d.vocab, e->tokens + 1LL * s * B, st));
   }
   if (n_new > 0 && a->tokens_out_dev) {  // [n_new, B] -> [B, n_new]
     for (int s = 0; s < n_new; ++s)
       CUDA_TRY(cudaMemcpy2DAsync(a->tokens_out_dev + s, sizeof(long long) * n_new, e->tokens + 1LL * s * B,
                                  sizeof(long long), sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
   }
+  return 0;
+}
+
+// Small batches are launch-bound (~2000 kernels per pass): the whole pass is captured once per distinct argument set
+// into a CUDA graph on the engine's own stream and replayed afterwards.  The first call with a new key runs eagerly
+// (it also performs the one-time cudaFuncSetAttribute calls), the second captures, later calls replay.
+extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
+  if (!e || !a) return set_error("ovla_run: null argument");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  if (a->B <= 0 || a->B > e->graph_max_batch || prof_enabled()) return run_impl(e, a, user);
+  CUDA_TRY(cudaSetDevice(e->device));
+  GraphKey key;
+  memset(&key, 0, sizeof(key));  // field-wise copy keeps the padding bytes zero for the memcmp ordering
+  key.a.input_ids_dev = a->input_ids_dev; key.a.pixel_values_dev = a->pixel_values_dev;
+  key.a.B = a->B; key.a.P = a->P; key.a.pool_len = a->pool_len; key.a.pool_mode = a->pool_mode;
+  key.a.n_new_tokens = a->n_new_tokens; key.a.pooled_out_dev = a->pooled_out_dev;
+  key.a.tokens_out_dev = a->tokens_out_dev; key.a.step_logits_out_dev = a->step_logits_out_dev;
+  key.a.hidden_out_dev = a->hidden_out_dev; key.a.projector_out_dev = a->projector_out_dev;
+  key.a.patches_out_dev = a->patches_out_dev;
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    if (e->graphs.size() >= 16) {  // bounded cache: drop everything (keys are few in steady state)
+      for (auto& kv : e->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      e->graphs.clear();
+    }
+    e->graphs.emplace(key, GraphEntry{});
+    return run_impl(e, a, user);
+  }
+  GraphEntry& g = it->second;
+  if (!g.exec) {
+    if (!e->own_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    }
+    const long long before = launch_count();
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_impl(e, a, e->own_stream);
+    const cudaError_t ce = cudaStreamEndCapture(e->own_stream, &graph);
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      e->graphs.erase(it);
+      if (rc != 0) return -1;
+      return run_impl(e, a, user);  // capture unsupported here: stay eager
+    }
+    g.launches = launch_count() - before;
+    count_launch(-static_cast<int>(g.launches));  // capture recorded the kernels, it did not run them
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      g.exec = nullptr;
+      cudaGetLastError();
+      e->graphs.erase(it);
+      return run_impl(e, a, user);
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e->ev_in, user));
+  CUDA_TRY(cudaStreamWaitEvent(e->own_stream, e->ev_in, 0));
+  CUDA_TRY(cudaGraphLaunch(g.exec, e->own_stream));
+  CUDA_TRY(cudaEventRecord(e->ev_out, e->own_stream));
+  CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
+  count_launch(static_cast<int>(g.launches));
   return 0;
 }
 

@@ -89,10 +89,19 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (mode == kModeBf16 && (N % 8)) return set_error("gemm: N=%d must be a multiple of 8", N);
   if (mode == kModeSwiGLU && (N % 64)) return set_error("gemm: SwiGLU N=%d must be a multiple of 64", N);
   if (mode == kModeF32 && (N % 4)) return set_error("gemm: N=%d must be a multiple of 4", N);
-  if (bn <= 0) {  // heuristic: biggest tile that still gives every SM work
+  if (bn <= 0) {
+    // Tile heuristic.  Large problems: CTA-pair 256x256 tiles (tensor-bound).  Small M (bs=1 prefill, M = 261..288,
+    // and the batched decode steps, M = B): the GEMM is a weight stream whose speed is set by shared-memory fill
+    // traffic (every CTA re-loads the activation tile), so wide single-CTA tiles win
+    // (tools/gemm_smallm_bench.py, profiles/r01_gemm_smallm.jsonl).
     const long long t256 = ((M + 255LL) / 256) * ((N + 255LL) / 256);
-    if (t256 * 2 >= num_sms) { bn = 256; cg = 2; }
-    else if (((M + 127LL) / 128) * ((N + 127LL) / 128) >= num_sms) { bn = 128; cg = 1; }
+    const int m128 = (M + 127) / 128, m256 = (M + 255) / 256;
+    if (M <= 512) {
+      if (N >= 8192) { bn = 256; cg = (m256 * 2 == m128) ? 2 : 1; }   // a CTA pair only if it adds no empty 128-row tile
+      else { bn = (m128 >= 3) ? 128 : 64; cg = 1; }
+    }
+    else if (t256 * 2 >= num_sms) { bn = 256; cg = 2; }
+    else if (1LL * m128 * ((N + 127LL) / 128) >= num_sms) { bn = 128; cg = 1; }
     else { bn = 64; cg = 1; }
   }
   if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");

@@ -1,13 +1,25 @@
 // Skinny GEMM for the batch<=8 cached decode steps (modeling_prismatic.py:325-341 -> LlamaForCausalLM decode):
 //   out[m, n] = sum_k x[m, k] * W[n, k],  m < M <= 8.
-// Pure weight streaming: every weight byte is read exactly once with 16-byte loads (L1 no-allocate), one warp per
-// output column, 4 independent loads in flight per lane; the M activation rows (<= 176 KB total) stay L1/L2
-// resident.  Same epilogues (and rounding points) as the tcgen05 GEMM.
+// Pure weight streaming: every weight byte is read exactly once with 16-byte L1-bypassing loads; one warp per output
+// column; the loads are software-pipelined (the next 4 chunks are in flight while the current 4 are consumed), small
+// register footprint so that ~32 warps per SM keep > 64 KB of loads in flight.  The M activation rows (<= 176 KB in
+// total) are read through L1.  Launched with programmatic dependent launch: the first weight chunks are fetched
+// before the dependency wait, i.e. while the preceding kernel is still finishing.  Same epilogues / rounding points
+// as the tcgen05 GEMM.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
 
 namespace ovla {
+
+static constexpr int kGemvThreadsDefault = 128;
+
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
@@ -18,46 +30,45 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 }
 
 template <int MB>
-__device__ __forceinline__ void dot_row(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ x,
-                                        long long ldx, int M, int K, int lane, float* acc) {
+__device__ __forceinline__ void fma_chunk(const uint4& wv, const __nv_bfloat16* __restrict__ x, long long ldx, int M,
+                                          int col, float* acc) {
+  const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (m < M ? m : M - 1) * ldx + col));
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16(ww[j]), b = unpack_bf16(xw[j]);
+      acc[m] = fmaf(a.x, b.x, acc[m]);
+      acc[m] = fmaf(a.y, b.y, acc[m]);
+    }
+  }
+}
+
+template <int kCh>
+__device__ __forceinline__ void load_stage(uint4* dst, const __nv_bfloat16* __restrict__ w, int i, int kv) {
+#pragma unroll
+  for (int u = 0; u < kCh; ++u)
+    if (i + 32 * u < kv) dst[u] = ldg_stream(w + (i + 32 * u) * 8);
+}
+
+// dot products of one weight row with the M activation rows; `cur` already holds the row's first stage
+template <int MB, int kCh>
+__device__ __forceinline__ void dot_row(const __nv_bfloat16* __restrict__ w, uint4* cur,
+                                        const __nv_bfloat16* __restrict__ x, long long ldx, int M, int K, int lane,
+                                        float* acc) {
 #pragma unroll
   for (int m = 0; m < MB; ++m) acc[m] = 0.f;
   const int kv = K / 8;
-  int i = lane;
-  for (; i + 96 < kv; i += 128) {
-    uint4 wv[4];
+  for (int i = lane; i < kv; i += 32 * kCh) {
+    uint4 nxt[kCh];
+    load_stage<kCh>(nxt, w, i + 32 * kCh, kv);  // next stage in flight while this one is consumed
 #pragma unroll
-    for (int u = 0; u < 4; ++u) wv[u] = ldg_stream(w + (i + 32 * u) * 8);
+    for (int u = 0; u < kCh; ++u)
+      if (i + 32 * u < kv) fma_chunk<MB>(cur[u], x, ldx, M, (i + 32 * u) * 8, acc);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
-#pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(x + (m < M ? m : M - 1) * ldx + (i + 32 * u) * 8);
-        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_bf16(ww[j]), b = unpack_bf16(xw[j]);
-          acc[m] = fmaf(a.x, b.x, acc[m]);
-          acc[m] = fmaf(a.y, b.y, acc[m]);
-        }
-      }
-    }
-  }
-  for (; i < kv; i += 32) {
-    const uint4 wv = ldg_stream(w + i * 8);
-    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(x + (m < M ? m : M - 1) * ldx + i * 8);
-      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16(ww[j]), b = unpack_bf16(xw[j]);
-        acc[m] = fmaf(a.x, b.x, acc[m]);
-        acc[m] = fmaf(a.y, b.y, acc[m]);
-      }
-    }
+    for (int u = 0; u < kCh; ++u) cur[u] = nxt[u];
   }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
@@ -66,22 +77,33 @@ __device__ __forceinline__ void dot_row(const __nv_bfloat16* __restrict__ w, con
   }
 }
 
-template <int MB, int MODE>
+template <int MB, int MODE, int kCh>
 __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                   const __nv_bfloat16* __restrict__ W, long long ldw, int M, int N,
-                                                   int K, GemmEpi epi) {
+                                                            const __nv_bfloat16* __restrict__ W, long long ldw, int M,
+                                                            int N, int K, GemmEpi epi) {
   const int lane = threadIdx.x & 31;
   const int warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * (blockDim.x >> 5);
   const int n_out = (MODE == kModeSwiGLU) ? N / 2 : N;
+  const int kv = K / 8;
+  auto row_of = [](int n) -> long long {
+    return (MODE == kModeSwiGLU) ? static_cast<long long>(n / 32) * 64 + (n % 32) : n;
+  };
+  // weights do not depend on the previous kernel: the first stage of this warp's first row is fetched before the
+  // dependency wait and overlaps the predecessor's tail
+  uint4 cur[kCh];
+  if (warp_g < n_out) load_stage<kCh>(cur, W + row_of(warp_g) * ldw, lane, kv);
+  griddep_launch_dependents();
+  griddep_wait();  // activations / residual written by the predecessor are complete and visible from here on
+
   for (int n = warp_g; n < n_out; n += n_warps) {
     float acc[MB], acc2[MB];
+    const long long r = row_of(n);
+    if (n != warp_g) load_stage<kCh>(cur, W + r * ldw, lane, kv);
+    dot_row<MB, kCh>(W + r * ldw, cur, x, ldx, M, K, lane, acc);
     if (MODE == kModeSwiGLU) {
-      const long long rg = static_cast<long long>(n / 32) * 64 + (n % 32);
-      dot_row<MB>(W + rg * ldw, x, ldx, M, K, lane, acc);
-      dot_row<MB>(W + (rg + 32) * ldw, x, ldx, M, K, lane, acc2);
-    } else {
-      dot_row<MB>(W + static_cast<long long>(n) * ldw, x, ldx, M, K, lane, acc);
+      load_stage<kCh>(cur, W + (r + 32) * ldw, lane, kv);
+      dot_row<MB, kCh>(W + (r + 32) * ldw, cur, x, ldx, M, K, lane, acc2);
     }
     if (lane == 0) {
 #pragma unroll
@@ -110,23 +132,65 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
   }
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+// tuning knobs (defaults chosen from tools/gemv_microbench.py on B200; see profiles/)
+static int gemv_threads() { static int v = env_int("OVLA_GEMV_THREADS", kGemvThreadsDefault); return v; }
+static int gemv_ch() { static int v = env_int("OVLA_GEMV_CH", 4); return v; }
+static int gemv_bps() { static int v = env_int("OVLA_GEMV_BPS", 16); return v; }
+
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OVLA_GEMV_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int MB, int MODE, int kCh>
+static int gemv_launch_t(const __nv_bfloat16* X, long long ldx, const __nv_bfloat16* Wp, long long ldw, int M, int N,
+                         int K, const GemmEpi& epi, int blocks, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(gemv_threads());
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr_pdl[1];
+  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr_pdl;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemv_kernel<MB, MODE, kCh>, X, ldx, Wp, ldw, M, N, K, epi));
+  count_launch();
+  return 0;
+}
+
 template <int MODE>
 static int gemv_dispatch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K,
                          const GemmEpi& epi, cudaStream_t st) {
   const int n_out = (MODE == kModeSwiGLU) ? N / 2 : N;
-  int blocks = (n_out + 7) / 8;
-  const int max_blocks = num_sms() * 8;
+  const int wpb = gemv_threads() / 32;
+  int blocks = (n_out + wpb - 1) / wpb;
+  const int max_blocks = num_sms() * gemv_bps();
   if (blocks > max_blocks) blocks = max_blocks;
   auto X = static_cast<const __nv_bfloat16*>(x);
   auto Wp = static_cast<const __nv_bfloat16*>(W);
   ProfScope prof(kCatGemv, 2.0 * M * N * K, 2.0 * N * K + 2.0 * M * (K + n_out), st);
-  if (M <= 1) gemv_kernel<1, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
-  else if (M <= 2) gemv_kernel<2, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
-  else if (M <= 4) gemv_kernel<4, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
-  else gemv_kernel<8, MODE><<<blocks, 256, 0, st>>>(X, ldx, Wp, ldw, M, N, K, epi);
-  CUDA_TRY(cudaGetLastError());
-  count_launch();
-  return 0;
+  const int ch = gemv_ch();
+#define OVLA_GEMV_CASE(MBV)                                                                          \
+  {                                                                                                  \
+    if (ch == 2) return gemv_launch_t<MBV, MODE, 2>(X, ldx, Wp, ldw, M, N, K, epi, blocks, st);      \
+    if (ch == 8) return gemv_launch_t<MBV, MODE, 8>(X, ldx, Wp, ldw, M, N, K, epi, blocks, st);      \
+    return gemv_launch_t<MBV, MODE, 4>(X, ldx, Wp, ldw, M, N, K, epi, blocks, st);                   \
+  }
+  if (M <= 1) OVLA_GEMV_CASE(1)
+  if (M <= 2) OVLA_GEMV_CASE(2)
+  if (M <= 4) OVLA_GEMV_CASE(4)
+  OVLA_GEMV_CASE(8)
+#undef OVLA_GEMV_CASE
 }
 
 int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, int mode,

@@ -16,6 +16,10 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
 // gemv.cu -- M <= 8 weight streaming
 int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, int mode,
                 const GemmEpi& epi, cudaStream_t st);
+// decode.cu -- fused RoPE + KV append + single-query attention
+int decode_rope_attn_launch(const void* qkv, long long qkv_ld, const void* cos_t, const void* sin_t, int pos, void* kc,
+                            void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
+                            cudaStream_t st);
 
 // norm.cu
 int layernorm_launch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
