@@ -11,6 +11,17 @@ def pair(kind="tiny", fused=True, llm_layers=2, depth=(3, 3)):
     if kind == "tiny":
         od = O.tiny_dims(fused=fused, llm_layers=llm_layers, depth=depth)
         pc = C.tiny(fused=fused, llm_layers=llm_layers, depth=depth)
+    elif kind == "full-width":
+        # real layer widths (1024 / 1152 / 4304 / 4096 / 11008, 224 px, T = 288) with shallow depth: exercises the
+        # full-size kernel shapes while the CPU oracle still finishes in seconds
+        import dataclasses
+        dino = O.TowerDims(1024, 3, 16, 4096, 5, True)
+        sig = O.TowerDims(1152, 3, 16, 4304, 0, False)
+        od = dataclasses.replace(O.OPENVLA_7B, towers=(dino, sig), llm_layers=llm_layers)
+        base = C.openvla_7b()
+        pc = dataclasses.replace(
+            base, towers=(dataclasses.replace(C.DINOV2_L14_REG4, depth=3), dataclasses.replace(C.SIGLIP_SO400M_14, depth=3)),
+            text_config=dataclasses.replace(base.text_config, num_hidden_layers=llm_layers))
     elif kind == "openvla-7b":
         od, pc = O.OPENVLA_7B, C.openvla_7b()
     elif kind == "siglip-7b":

@@ -1,0 +1,275 @@
+"""Operator-level GPU parity: every C-ABI kernel against the CPU oracle's definition of the same op on seeded inputs,
+including the awkward shapes of the real model (K = 588->592, N = 4304, head_dim 72, 261 tokens, ragged tails).
+
+Tolerances (stated): bf16 outputs are compared with the oracle computed in fp32 from the same bf16 inputs and then
+rounded to bf16 -- max error <= 2 bf16 ulps of the row scale (accumulation order differs, rounding points do not);
+integer / index results (argmax, de-tokeniser table) are bit-exact; fp64 de-tokenise / un-normalise is bit-exact.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import openvla_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from openvla_probe_b200 import _lib
+
+    return _lib, _lib.load()
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def close_bf16(got, ref32, ulps=2.0):
+    """|got - bf16(ref)| <= ulps * 2^-8 * max(|ref| row scale)."""
+    got, ref32 = got.float().cpu(), ref32.float().cpu()
+    scale = ref32.abs().amax(dim=-1, keepdim=True).clamp_min(1e-6)
+    err = (got - ref32).abs() / scale
+    return float(err.max()) <= ulps * 2.0 ** -8, float(err.max())
+
+
+# ----------------------------------------------------------------------------------------------- GEMM epilogues
+@pytest.mark.parametrize("M,N,K,bn,cg", [(512, 4304, 1152, 0, 0), (261 * 2, 1024, 4096, 128, 1), (256, 1152, 592, 64, 1),
+                                         (1024, 1024, 1024, 256, 2), (130, 3456, 1152, 128, 2)])
+def test_gemm_bias_gelu_scale_residual(L, M, N, K, bn, cg):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(M + N)
+    A = bf(torch.randn(M, K, generator=g) * 0.5)
+    W = bf(torch.randn(N, K, generator=g) * 0.05)
+    bias, scale, resid = bf(torch.randn(N, generator=g) * 0.1), bf(1 + 0.1 * torch.randn(N, generator=g)), bf(torch.randn(M, N, generator=g))
+    for gelu, use_scale, use_res in [(0, 0, 0), (1, 0, 0), (0, 1, 1), (0, 0, 1)]:
+        ref = F.linear(A.float(), W.float(), bias.float()).bfloat16().float()
+        if gelu:
+            ref = F.gelu(ref).bfloat16().float()
+        if use_scale:
+            ref = (ref * scale.float()).bfloat16().float()
+        if use_res:
+            ref = ref + resid.float()
+        Ad, Wd, bd, sd, rd = A.cuda(), W.cuda(), bias.cuda(), scale.cuda(), resid.cuda()
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        epi = _lib.GemmEpilogue()
+        epi.bias_bf16, epi.gelu = bd.data_ptr(), gelu
+        if use_scale:
+            epi.scale_bf16 = sd.data_ptr()
+        if use_res:
+            epi.resid_bf16, epi.ld_resid = rd.data_ptr(), N
+        _lib.check(lib.ovla_gemm(P(Ad), C.c_longlong(K), P(Wd), C.c_longlong(K), M, N, K, 0, 0, P(out), C.c_longlong(N),
+                                 C.byref(epi), bn, cg, None))
+        ok, e = close_bf16(out, ref, ulps=3.0)
+        assert ok, (gelu, use_scale, use_res, e)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8, 77, 300])
+def test_swiglu_and_fp32_logits_gemm_and_gemv_agree_with_oracle(L, M):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(M)
+    K, I, V = 256, 704, 32064
+    x = bf(torch.randn(M, K, generator=g))
+    Wg, Wu = bf(torch.randn(I, K, generator=g) * 0.06), bf(torch.randn(I, K, generator=g) * 0.06)
+    ref = (F.silu(F.linear(x.float(), Wg.float()).bfloat16().float()).bfloat16().float()
+           * F.linear(x.float(), Wu.float()).bfloat16().float())
+    Wi = torch.stack([Wg.view(I // 32, 32, K), Wu.view(I // 32, 32, K)], 1).reshape(2 * I, K).contiguous()
+    out = torch.empty(M, I, dtype=torch.bfloat16, device="cuda")
+    epi = _lib.GemmEpilogue()
+    xd, Wd = x.cuda(), Wi.cuda()
+    if M <= 8:
+        _lib.check(lib.ovla_gemv(P(xd), C.c_longlong(K), P(Wd), C.c_longlong(K), M, 2 * I, K, 1, P(out), C.c_longlong(I),
+                                 C.byref(epi), None))
+    else:
+        _lib.check(lib.ovla_gemm(P(xd), C.c_longlong(K), P(Wd), C.c_longlong(K), M, 2 * I, K, 1, 0, P(out), C.c_longlong(I),
+                                 C.byref(epi), 0, 0, None))
+    ok, e = close_bf16(out, ref, ulps=3.0)
+    assert ok, e
+    # lm_head: fp32 storage of bf16-rounded logits (HF `.float()`), vocab 32064 = 501 * 64
+    Wl = bf(torch.randn(V, K, generator=g) * 0.05)
+    refl = F.linear(x.float(), Wl.float()).bfloat16().float()
+    lg = torch.empty(M, V, dtype=torch.float32, device="cuda")
+    epi = _lib.GemmEpilogue()
+    epi.round_bf16 = 1
+    Wld = Wl.cuda()
+    if M <= 8:
+        _lib.check(lib.ovla_gemv(P(xd), C.c_longlong(K), P(Wld), C.c_longlong(K), M, V, K, 2, P(lg), C.c_longlong(V),
+                                 C.byref(epi), None))
+    else:
+        _lib.check(lib.ovla_gemm(P(xd), C.c_longlong(K), P(Wld), C.c_longlong(K), M, V, K, 2, 0, P(lg), C.c_longlong(V),
+                                 C.byref(epi), 0, 0, None))
+    assert torch.equal(lg.cpu().bfloat16().float(), lg.cpu())          # values are exactly representable in bf16
+    ok, e = close_bf16(lg, refl, ulps=2.0)
+    assert ok, e
+
+
+def test_gemm_rejects_bad_shapes(L):
+    _lib, lib = L
+    a = torch.zeros(16, 24, dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros(16, 24, dtype=torch.bfloat16, device="cuda")
+    epi = _lib.GemmEpilogue()
+    assert lib.ovla_gemm(P(a), C.c_longlong(24), P(a), C.c_longlong(24), 16, 12, 24, 0, 0, P(o), C.c_longlong(12), C.byref(epi), 0, 0, None) != 0
+    assert b"multiple of 8" in lib.ovla_last_error()
+    assert lib.ovla_gemm(P(a), C.c_longlong(20), P(a), C.c_longlong(24), 16, 16, 20, 0, 0, P(o), C.c_longlong(16), C.byref(epi), 0, 0, None) != 0
+    assert lib.ovla_gemm(P(a), C.c_longlong(24), P(a), C.c_longlong(24), 0, 16, 24, 0, 0, P(o), C.c_longlong(16), C.byref(epi), 0, 0, None) != 0
+
+
+# ----------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("rows,D", [(5, 128), (261, 1024), (300, 1152), (7, 4096), (1, 256)])
+def test_layernorm_and_rmsnorm(L, rows, D):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(D + rows)
+    x = bf(torch.randn(rows, D, generator=g) * 3 + 0.5)
+    w, b = bf(1 + 0.1 * torch.randn(D, generator=g)), bf(0.1 * torch.randn(D, generator=g))
+    out = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()          # keep device copies alive across the calls
+    _lib.check(lib.ovla_layernorm(P(xd), C.c_longlong(D), P(wd), P(bd), C.c_float(1e-6), P(out),
+                                  C.c_longlong(D), rows, D, None))
+    ref = F.layer_norm(x.float(), (D,), w.float(), b.float(), eps=1e-6)
+    ok, e = close_bf16(out, ref)
+    assert ok, e
+    _lib.check(lib.ovla_rmsnorm(P(xd), C.c_longlong(D), P(wd), C.c_float(1e-6), P(out), C.c_longlong(D), rows,
+                                D, None))
+    ref = O.rms_norm(x, w, 1e-6)                      # oracle in bf16: the reference's exact rounding points
+    assert float((out.cpu().float() - ref.float()).abs().max()) <= 2.0 ** -7 * float(ref.float().abs().max())
+    mism = (out.cpu() != ref).float().mean().item()
+    assert mism < 0.01                                # identical up to fp32 reduction-order effects on rsqrt
+
+
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,H,T,hd,causal", [(2, 2, 21, 64, 0), (1, 16, 261, 64, 0), (2, 16, 256, 72, 0), (1, 3, 16, 72, 0),
+                                             (2, 4, 288, 128, 1), (3, 2, 25, 128, 1), (1, 2, 130, 128, 1)])
+def test_flash_attention_vs_oracle(L, B, H, T, hd, causal):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(T * hd)
+    D = H * hd
+    qkv = bf(torch.randn(B, T, 3, H, hd, generator=g))
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]           # [B,H,T,hd]
+    ref = O._sdpa(q.float(), k.float(), v.float(), causal=bool(causal)).permute(0, 2, 1, 3).reshape(B, T, D)
+    buf = qkv.reshape(B * T, 3 * D).contiguous().cuda()
+    out = torch.empty(B * T, D, dtype=torch.bfloat16, device="cuda")
+    s = (C.c_longlong * 12)(3 * D * T, 3 * D, hd, 3 * D * T, 3 * D, hd, 3 * D * T, 3 * D, hd, D * T, D, hd)
+    kq = C.c_void_p(buf.data_ptr() + 2 * D)
+    vq = C.c_void_p(buf.data_ptr() + 4 * D)
+    _lib.check(lib.ovla_flash_attention(P(buf), kq, vq, P(out), s, B, H, T, T, hd, causal, None))
+    got = out.view(B, T, D).float().cpu()
+    assert float((got - ref).abs().max()) <= 0.03 * float(ref.abs().max()) + 1e-3
+    assert float((got - ref).norm() / ref.norm()) < 6e-3
+
+
+@pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])
+def test_decode_rope_attention_and_cache_append(L, B, ctx):
+    """Fused RoPE + KV append + 1-query attention == oracle llama attention step with a KV cache."""
+    _lib, lib = L
+    from openvla_probe_b200.engine import rope_tables
+
+    H, hd, Tmax = 4, 128, 304
+    D = H * hd
+    g = torch.Generator().manual_seed(ctx)
+    pos = ctx - 1
+    kc = bf(torch.randn(B, H, Tmax, hd, generator=g))
+    vc = bf(torch.randn(B, H, Tmax, hd, generator=g))
+    qkv = bf(torch.randn(B, 3 * D, generator=g))
+    cos, sin = rope_tables(hd, 10000.0, Tmax)
+    d = O.VLADims(llm_dim=D, llm_heads=H)
+    c_full, s_full = O.rope_cos_sin(d, torch.tensor([pos]), torch.bfloat16)
+    q = qkv[:, :D].view(B, 1, H, hd).transpose(1, 2)
+    k = qkv[:, D:2 * D].view(B, 1, H, hd).transpose(1, 2)
+    v = qkv[:, 2 * D:].view(B, 1, H, hd).transpose(1, 2)
+    q_r = q * c_full + O._rotate_half(q) * s_full
+    k_r = k * c_full + O._rotate_half(k) * s_full
+    K_all = torch.cat([kc[:, :, :pos], k_r], 2)
+    V_all = torch.cat([vc[:, :, :pos], v], 2)
+    ref = O._sdpa(q_r, K_all, V_all, causal=True, q_offset=pos).transpose(1, 2).reshape(B, D)
+    kcd, vcd, qd, cd, sd = kc.cuda(), vc.cuda(), qkv.cuda(), cos.cuda(), sin.cuda()
+    out = torch.empty(B, D, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.ovla_decode_rope_attention(P(qd), C.c_longlong(3 * D), P(cd), P(sd), pos, P(kcd),
+                                              P(vcd), B, H, hd, Tmax, P(out), C.c_longlong(D), None))
+    assert torch.equal(kcd[:, :, pos].cpu(), k_r[:, :, 0])               # rotated key appended bit-exactly
+    assert torch.equal(vcd[:, :, pos].cpu(), v[:, :, 0])
+    assert torch.equal(kcd[:, :, :pos].cpu(), kc[:, :, :pos])            # older entries untouched
+    got = out.float().cpu()
+    assert float((got - ref.float()).abs().max()) <= 0.03 * float(ref.float().abs().max()) + 1e-3
+
+
+def test_rope_kv_prefill_bit_exact(L):
+    _lib, lib = L
+    from openvla_probe_b200.engine import rope_tables
+
+    B, T, H, hd, Tmax = 2, 19, 3, 128, 40
+    D = H * hd
+    g = torch.Generator().manual_seed(0)
+    qkv = bf(torch.randn(B * T, 3 * D, generator=g))
+    cos, sin = rope_tables(hd, 10000.0, Tmax)
+    d = O.VLADims(llm_dim=D, llm_heads=H)
+    c, s = O.rope_cos_sin(d, torch.arange(T), torch.bfloat16)
+    x = qkv.view(B, T, 3, H, hd)
+    q_ref = x[:, :, 0] * c[None, :, None] + O._rotate_half(x[:, :, 0]) * s[None, :, None]
+    k_ref = x[:, :, 1] * c[None, :, None] + O._rotate_half(x[:, :, 1]) * s[None, :, None]
+    buf = qkv.clone().cuda()
+    kc = torch.zeros(B, H, Tmax, hd, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    cd, sd = cos.cuda(), sin.cuda()
+    _lib.check(lib.ovla_rope_kv(P(buf), B, T, H, hd, 0, P(cd), P(sd), P(kc), P(vc), Tmax, None))
+    assert torch.equal(buf.cpu().view(B, T, 3, H, hd)[:, :, 0], q_ref)
+    assert torch.equal(kc.cpu()[:, :, :T].permute(0, 2, 1, 3), k_ref)
+    assert torch.equal(vc.cpu()[:, :, :T].permute(0, 2, 1, 3), x[:, :, 2])
+    assert lib.ovla_rope_kv(P(buf), B, T, H, hd, 30, P(cd), P(sd), P(kc), P(vc), Tmax, None) != 0  # overflow
+
+
+# ----------------------------------------------------------------------------------------------- capture / argmax / detok
+@pytest.mark.parametrize("B,T,D,n", [(1, 7, 256, 7), (3, 288, 4096, 287), (2, 33, 264, 1)])
+def test_pool_tokens_mean_and_final(L, B, T, D, n):
+    _lib, lib = L
+    x = bf(torch.randn(B, T, D, generator=torch.Generator().manual_seed(T)))
+    out = torch.empty(B, D, dtype=torch.float32, device="cuda")
+    xd = x.cuda()
+    for mode, ref in ((0, x[:, :n].float().mean(1)), (1, x[:, n - 1].float())):
+        _lib.check(lib.ovla_pool_tokens(P(xd), C.c_longlong(T * D), C.c_longlong(D), B, n, D, mode, P(out),
+                                        C.c_longlong(D), None))
+        assert torch.allclose(out.cpu(), ref, rtol=0, atol=2e-6 * max(1.0, float(ref.abs().max())) * math.sqrt(n))
+    assert lib.ovla_pool_tokens(P(xd), C.c_longlong(T * D), C.c_longlong(D), B, 0, D, 0, P(out), C.c_longlong(D), None) != 0
+
+
+def test_argmax_bit_exact_ties_nan_inf(L):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(0)
+    V = 32064
+    x = torch.randn(9, V, generator=g).bfloat16().float()             # bf16-rounded values -> many exact ties
+    x[1, 31990] = x[1].max()
+    x[1, 17] = x[1].max()                                             # tie: lowest index wins
+    x[2, :] = 0.0                                                     # all equal -> index 0
+    x[3, 32063] = float("inf")
+    x[4, 5] = float("nan")
+    x[4, 9] = float("inf")                                            # NaN counts as maximum
+    x[5, :] = float("-inf")
+    x[6, 32000:] = 100.0                                              # padding rows can win; first one reported
+    out = torch.empty(9, dtype=torch.int64, device="cuda")
+    xd = x.cuda()
+    _lib.check(lib.ovla_argmax(P(xd), C.c_longlong(V), 9, V, P(out), None))
+    assert out.cpu().tolist() == torch.argmax(x, dim=-1).tolist()
+    assert lib.ovla_argmax(P(xd), C.c_longlong(V), 9, 0, P(out), None) != 0
+
+
+def test_detokenize_unnormalize_bit_exact_all_ids(L):
+    _lib, lib = L
+    ids = np.arange(0, 32064, dtype=np.int64)
+    ids = np.concatenate([ids, ids[:1]])                               # 32065 = 7 * 4580 + 5 -> pad to a multiple of 7
+    ids = np.concatenate([ids, np.full(7 - len(ids) % 7, 31900, dtype=np.int64)])
+    stats = O.default_stats()
+    ref = O.unnormalize(O.detokenize(ids.reshape(-1, 7)), stats)
+    _, centers = O.action_bins(256)
+    q01, q99 = np.asarray(stats["q01"]), np.asarray(stats["q99"])
+    mask = np.asarray(stats["mask"], dtype=np.uint8)
+    ids_d, c_d, lo_d, hi_d, m_d = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (ids, centers, q01, q99, mask)]
+    out = torch.empty(len(ids), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ovla_detokenize(P(ids_d), len(ids), 7, 32000, P(c_d), 255, P(lo_d), P(hi_d), P(m_d), P(out), None))
+    assert np.array_equal(out.cpu().numpy().reshape(-1, 7), ref)       # float64, bit for bit

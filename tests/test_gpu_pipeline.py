@@ -136,3 +136,24 @@ def test_error_behaviour():
     # empty batch
     a = model.predict_action(ids[:0], unnorm_key="synthetic", pixel_values=px[:0])
     assert a.shape == (0, 7)
+
+
+def test_full_width_shapes_against_fp32_oracle():
+    """Real layer widths / 224-px frames / T = 288 (depth cut to 3 ViT blocks + 2 Llama layers so the CPU oracle
+    finishes in seconds).  Stated tolerance vs the fp32 oracle: rel-L2 <= 1.5e-2 on pooled hidden states and on the
+    vision / projector outputs, <= 3e-2 on last-position logits (bf16 pipeline, ~30 rounding points deep)."""
+    od, pc, W, model, ids, px = _build(kind="full-width", B=2, P=31, llm_layers=2)
+    ids29 = torch.cat([ids, torch.full((2, 1), 29871)], 1)
+    r = model.engine.run(ids29, px, od.n_patches + 31, 0, 2, want_logits=True, want_patches=True, want_projector=True)
+    with torch.no_grad():
+        W32 = to_f32(W)
+        patches = O.vision_backbone(W32, od, px.float())
+        out = O.multimodal_forward(W32, od, ids29, px, dtype=torch.float32)
+    assert rel_l2(r["patches"].float().cpu(), patches) < 1.5e-2
+    assert rel_l2(r["projector"].float().cpu(), out.projector_features) < 1.5e-2
+    pooled = r["pooled"].cpu()
+    for i, h in enumerate(out.hidden_states):
+        ref = h[:, : od.n_patches + 31].mean(1)
+        assert rel_l2(pooled[i], ref) < 1.5e-2, i
+    assert rel_l2(r["step_logits"][0].cpu(), out.logits[:, -1]) < 3e-2
+    assert torch.equal(r["tokens"].cpu(), torch.argmax(r["step_logits"].cpu(), -1).t())
