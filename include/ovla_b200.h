@@ -88,6 +88,12 @@ int ovla_argmax(const float* logits_dev, long long ld, int rows, int n, long lon
 int ovla_detokenize(const long long* ids_dev, int n, int action_dim, int vocab_size, const double* centers_dev,
                     int n_centers, const double* q01_dev, const double* q99_dev, const unsigned char* mask_dev,
                     double* out_dev, void* stream);
+/* Fused Llama QKV projection for the prefill (LlamaAttention.forward: q/k/v_proj + apply_rotary_pos_emb + cache update):
+ * [M = B*T, K] x [3*H*128, K]^T; RoPE(q) is written to qkv_out[:, 0:H*128] (pitch ldo), RoPE(k) and v go straight into
+ * the KV cache [B, H, Tmax, 128] at position pos0 + (row % T).  Rounding points as the reference's bf16 ops. */
+int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K, int T,
+                       int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev, long long ldo,
+                       void* k_cache_dev, void* v_cache_dev, int Tmax, int tile_n, int cta_group, void* stream);
 /* small-batch (M <= 8) weight-streaming GEMM with the same epilogues as ovla_gemm */
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream);

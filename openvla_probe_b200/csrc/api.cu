@@ -68,6 +68,24 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
 }
 
 
+int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K, int T,
+                       int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev, long long ldo,
+                       void* k_cache_dev, void* v_cache_dev, int Tmax, int tile_n, int cta_group, void* stream) {
+  GemmEpi e = {};
+  e.out = qkv_out_dev;
+  e.ldo = ldo;
+  e.rope_cos = static_cast<const __nv_bfloat16*>(cos_dev);
+  e.rope_sin = static_cast<const __nv_bfloat16*>(sin_dev);
+  e.k_cache = static_cast<__nv_bfloat16*>(k_cache_dev);
+  e.v_cache = static_cast<__nv_bfloat16*>(v_cache_dev);
+  e.T = T;
+  e.pos0 = pos0;
+  e.Tmax = Tmax;
+  e.H = H;
+  return gemm_launch(a_dev, lda, w_dev, ldw, M, 3 * H * 128, K, kModeQkvRope, kKindBf16, e, tile_n, cta_group, num_sms(),
+                     static_cast<cudaStream_t>(stream));
+}
+
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream) {
   return gemv_launch(x_dev, ldx, w_dev, ldw, M, N, K, mode, to_epi(out_dev, ldo, epi),

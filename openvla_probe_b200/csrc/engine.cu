@@ -90,6 +90,7 @@ struct OvlaEngine {
   int* err_flag = nullptr;
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
+  bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<GraphKey, GraphEntry> graphs;
@@ -146,6 +147,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   CUDA_TRY(cudaSetDevice(device));
   OvlaEngine* e = new OvlaEngine();
   e->d = *dims;
+  if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
   e->device = device;
   const OvlaDims& d = e->d;
   const int g = d.image_size / d.patch;
@@ -501,9 +503,24 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
                                sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, rows, D, st));
-    OVLA_TRY(linear(e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
-    OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
-                            Tmax, st));
+    if (e->fuse_rope) {  // QKV projection with RoPE + KV-cache write fused into the GEMM epilogue
+      GemmEpi epi = {};
+      epi.out = e->l_qkv;
+      epi.ldo = 3LL * D;
+      epi.rope_cos = e->rope_cos.ptr;
+      epi.rope_sin = e->rope_sin.ptr;
+      epi.k_cache = e->k_cache(i);
+      epi.v_cache = e->v_cache(i);
+      epi.T = T;
+      epi.pos0 = 0;
+      epi.Tmax = Tmax;
+      epi.H = H;
+      OVLA_TRY(gemm_launch(e->l_h, D, l.qkv_w.ptr, D, rows, 3 * D, D, kModeQkvRope, kKindBf16, epi, 0, 0, num_sms(), st));
+    } else {
+      OVLA_TRY(linear(e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
+      OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
+                              Tmax, st));
+    }
     OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
     OVLA_TRY(linear(e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));

@@ -1,4 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map encoding and launch dispatch.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "host_util.h"
 
@@ -89,6 +91,12 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (mode == kModeBf16 && (N % 8)) return set_error("gemm: N=%d must be a multiple of 8", N);
   if (mode == kModeSwiGLU && (N % 64)) return set_error("gemm: SwiGLU N=%d must be a multiple of 64", N);
   if (mode == kModeF32 && (N % 4)) return set_error("gemm: N=%d must be a multiple of 4", N);
+  if (mode == kModeQkvRope) {
+    if (N != 3 * epi.H * 128) return set_error("gemm: fused QKV+RoPE needs N = 3 * H * 128 (head_dim 128)");
+    if (!epi.rope_cos || !epi.rope_sin || !epi.k_cache || !epi.v_cache || epi.T <= 0 || (M % epi.T))
+      return set_error("gemm: fused QKV+RoPE needs cos/sin tables, KV caches and M = B * T");
+    if (epi.pos0 + epi.T > epi.Tmax) return set_error("gemm: position %d exceeds KV capacity %d", epi.pos0 + epi.T, epi.Tmax);
+  }
   if (bn <= 0) {
     // Tile heuristic.  Large problems: CTA-pair 256x256 tiles (tensor-bound).  Small M (bs=1 prefill, M = 261..288,
     // and the batched decode steps, M = B): the GEMM is a weight stream whose speed is set by shared-memory fill
@@ -105,14 +113,21 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     else { bn = 64; cg = 1; }
   }
   if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");
+  if (mode == kModeQkvRope && bn < 128) { bn = 128; cg = 1; }  // a tile must hold whole 128-wide heads
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, A, eb, M, K, lda, kBM)) return -1;
   if (make_tmap_2d(&tb, W, eb, N, K, ldw, bn / cg)) return -1;
-  GemmShape s{M, N, K};
+  // rasterisation group (tools/gemm_group_sweep.py, profiles/r01_gemm_group_sweep.jsonl): 16 row-tiles keep the
+  // activation slab of a group L2-resident while the weights stream; narrow, short-K problems prefer 8
+  static int g_group = -1;
+  if (g_group < 0) { const char* ev = getenv("OVLA_GEMM_GROUP"); g_group = (ev && atoi(ev) > 0) ? atoi(ev) : 0; }
+  const int group = g_group > 0 ? g_group : ((N <= 4096 && K <= 4096) ? 8 : 16);
+  GemmShape s{M, N, K, group};
   if (kind == kKindBf16) {
     if (mode == kModeBf16) return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
     if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
     if (mode == kModeF32) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
+    if (mode == kModeQkvRope) return dispatch_tile<kModeQkvRope, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
   } else {
     if (mode == kModeF32) return dispatch_tile<kModeF32, kKindTf32>(bn, cg, ta, tb, s, epi, num_sms, stream);
   }

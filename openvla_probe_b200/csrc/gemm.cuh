@@ -22,6 +22,7 @@ enum GemmMode : int {
   kModeBf16 = 0,    // bf16 out; optional bias / GELU / LayerScale / residual
   kModeSwiGLU = 1,  // W rows interleaved [32 gate | 32 up]; out[M, N/2] = silu(g) * u
   kModeF32 = 2,     // fp32 out; optional fp32-or-bf16 bias; optional rounding of the value to bf16
+  kModeQkvRope = 3, // fused Llama QKV projection: RoPE on q/k, q written back, rotated k and v written to the KV cache
 };
 enum GemmKind : int { kKindBf16 = 0, kKindTf32 = 1 };
 
@@ -35,10 +36,17 @@ struct GemmEpi {
   const float* bias_f32;
   int gelu;
   int round_bf16;
+  // kModeQkvRope only (head_dim 128): rows are (b, t) with t = row % T at position pos0 + t
+  const __nv_bfloat16* rope_cos;  // [Tmax, 64] bf16
+  const __nv_bfloat16* rope_sin;
+  __nv_bfloat16* k_cache;         // [B, H, Tmax, 128]
+  __nv_bfloat16* v_cache;
+  int T, pos0, Tmax, H;
 };
 
 struct GemmShape {
   int M, N, K;  // N = rows of W (pre-epilogue output columns); K in elements
+  int group_m;  // rasterisation group size (row-tiles)
 };
 
 static constexpr int kGemmThreads = 256;
@@ -55,8 +63,9 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int& mb, int& nb) {
-  constexpr int G = 8;
+// Tile rasterisation: groups of G row-tiles sweep all column-tiles, so that a wave of concurrent CTAs touches a
+// near-square block of the output and both operands are re-used from L2.
+__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int& mb, int& nb) {
   const int per_group = G * num_n;
   const int g = t / per_group;
   const int first_m = g * G;
@@ -126,7 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int t = worker; t < num_tiles; t += num_workers) {
         int mb, nb;
-        gemm_tile_coords(t, num_m, num_n, mb, nb);
+        gemm_tile_coords(t, num_m, num_n, shape.group_m, mb, nb);
         const int row_a = mb * kTileM + static_cast<int>(cta_rank) * kBM;
         const int row_b = nb * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -185,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     for (int t = worker; t < num_tiles; t += num_workers) {
       int mb, nb;
-      gemm_tile_coords(t, num_m, num_n, mb, nb);
+      gemm_tile_coords(t, num_m, num_n, shape.group_m, mb, nb);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
@@ -285,6 +294,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               o.z = pack_bf16(y[4], y[5]);
               o.w = pack_bf16(y[6], y[7]);
               *reinterpret_cast<uint4*>(out + cg) = o;
+            }
+          }
+        }
+      } else if constexpr (MODE == kModeQkvRope) {
+        // W = [q | k | v] rows, each [H, 128]; a 128-column group of the tile is one head of q, k or v.  rotate_half
+        // pairs column j with j + 64, i.e. 32-column chunk c with chunk c + 2 of the same head.  Rounding points as
+        // the reference's bf16 ops: linear output, each RoPE product, and the sum (modeling_llama apply_rotary_pos_emb).
+        const int bidx = row / epi.T, t = row - bidx * epi.T, pos = epi.pos0 + t;
+        const int Dm = epi.H * 128;
+        __nv_bfloat16* qrow = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
+#pragma unroll 1
+        for (int hh = 0; hh < BN / 128; ++hh) {
+          const int colh = col0 + hh * 128;
+          const int which = colh / Dm, h = (colh - which * Dm) >> 7;
+          const long long coff = ((static_cast<long long>(bidx) * epi.H + h) * epi.Tmax + pos) * 128;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t lo[32], hi[32];
+            tmem_ld32(taddr + hh * 128 + half * 32, lo);
+            tmem_ld32(taddr + hh * 128 + 64 + half * 32, hi);
+            tmem_ld_wait();
+            if (!row_ok || colh >= shape.N) continue;
+            __nv_bfloat16* d1;
+            if (which == 0) d1 = qrow + h * 128 + half * 32;
+            else if (which == 1) d1 = epi.k_cache + coff + half * 32;
+            else d1 = epi.v_cache + coff + half * 32;
+            const __nv_bfloat16* cs = epi.rope_cos + static_cast<long long>(pos) * 64 + half * 32;
+            const __nv_bfloat16* sn = epi.rope_sin + static_cast<long long>(pos) * 64 + half * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float o1[8], o2[8];
+              if (which < 2) {
+                const uint4 cu = *reinterpret_cast<const uint4*>(cs + g * 8);
+                const uint4 su = *reinterpret_cast<const uint4*>(sn + g * 8);
+                const uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 c = unpack_bf16(cw[i]), sI = unpack_bf16(sw[i]);
+                  const float a0 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i])), a1 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i + 1]));
+                  const float b0 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i])), b1 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i + 1]));
+                  o1[2 * i] = bf16_round(a0 * c.x) + bf16_round(-b0 * sI.x);
+                  o1[2 * i + 1] = bf16_round(a1 * c.y) + bf16_round(-b1 * sI.y);
+                  o2[2 * i] = bf16_round(b0 * c.x) + bf16_round(a0 * sI.x);
+                  o2[2 * i + 1] = bf16_round(b1 * c.y) + bf16_round(a1 * sI.y);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  o1[i] = __uint_as_float(lo[g * 8 + i]);
+                  o2[i] = __uint_as_float(hi[g * 8 + i]);
+                }
+              }
+              uint4 w1, w2;
+              w1.x = pack_bf16(o1[0], o1[1]); w1.y = pack_bf16(o1[2], o1[3]); w1.z = pack_bf16(o1[4], o1[5]); w1.w = pack_bf16(o1[6], o1[7]);
+              w2.x = pack_bf16(o2[0], o2[1]); w2.y = pack_bf16(o2[2], o2[3]); w2.z = pack_bf16(o2[4], o2[5]); w2.w = pack_bf16(o2[6], o2[7]);
+              *reinterpret_cast<uint4*>(d1 + g * 8) = w1;
+              *reinterpret_cast<uint4*>(d1 + 64 + g * 8) = w2;
             }
           }
         }

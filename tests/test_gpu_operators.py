@@ -273,3 +273,36 @@ def test_detokenize_unnormalize_bit_exact_all_ids(L):
     out = torch.empty(len(ids), dtype=torch.float64, device="cuda")
     _lib.check(lib.ovla_detokenize(P(ids_d), len(ids), 7, 32000, P(c_d), 255, P(lo_d), P(hi_d), P(m_d), P(out), None))
     assert np.array_equal(out.cpu().numpy().reshape(-1, 7), ref)       # float64, bit for bit
+
+
+@pytest.mark.parametrize("B,T,H,bn,cg", [(2, 19, 2, 0, 0), (3, 288, 4, 256, 2), (1, 130, 2, 128, 1), (2, 70, 2, 256, 1)])
+def test_fused_qkv_rope_gemm_equals_unfused_path(L, B, T, H, bn, cg):
+    """The fused QKV + RoPE + KV-write epilogue is bit-identical to GEMM followed by the stand-alone RoPE kernel
+    (which test_rope_kv_prefill_bit_exact pins bit-exactly to the oracle's bf16 rotary embedding)."""
+    _lib, lib = L
+    from openvla_probe_b200.engine import rope_tables
+
+    hd, Tmax, K = 128, T + 9, 256
+    D = H * hd
+    g = torch.Generator().manual_seed(T)
+    x = bf(torch.randn(B * T, K, generator=g)).cuda()
+    W = bf(torch.randn(3 * D, K, generator=g) * 0.08).cuda()
+    cos, sin = rope_tables(hd, 10000.0, Tmax)
+    cd, sd = cos.cuda(), sin.cuda()
+    # unfused: GEMM -> rope kernel
+    ref = torch.empty(B * T, 3 * D, dtype=torch.bfloat16, device="cuda")
+    epi = _lib.GemmEpilogue()
+    _lib.check(lib.ovla_gemm(P(x), C.c_longlong(K), P(W), C.c_longlong(K), B * T, 3 * D, K, 0, 0, P(ref), C.c_longlong(3 * D),
+                             C.byref(epi), bn, cg, None))
+    kc0 = torch.zeros(B, H, Tmax, hd, dtype=torch.bfloat16, device="cuda")
+    vc0 = torch.zeros_like(kc0)
+    _lib.check(lib.ovla_rope_kv(P(ref), B, T, H, hd, 3, P(cd), P(sd), P(kc0), P(vc0), Tmax, None))
+    # fused
+    out = torch.zeros(B * T, 3 * D, dtype=torch.bfloat16, device="cuda")
+    kc1, vc1 = torch.zeros_like(kc0), torch.zeros_like(kc0)
+    _lib.check(lib.ovla_qkv_rope_gemm(P(x), C.c_longlong(K), P(W), C.c_longlong(K), B * T, H, K, T, 3, P(cd), P(sd), P(out),
+                                      C.c_longlong(3 * D), P(kc1), P(vc1), Tmax, bn, cg, None))
+    assert torch.equal(out[:, :D], ref[:, :D])
+    assert torch.equal(kc1, kc0) and torch.equal(vc1, vc0)
+    assert lib.ovla_qkv_rope_gemm(P(x), C.c_longlong(K), P(W), C.c_longlong(K), B * T, H, K, T, 20, P(cd), P(sd), P(out),
+                                  C.c_longlong(3 * D), P(kc1), P(vc1), Tmax, bn, cg, None) != 0      # past KV capacity
