@@ -5,7 +5,9 @@
 //   acc: fp32 in TMEM, two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (tcgen05.ld -> registers -> fused math -> 16-byte global stores).
+// warps 4..11 = epilogue (tcgen05.ld -> registers -> fused math -> 16-byte global stores): two warps per TMEM lane
+// quarter, each taking every other 32-column chunk, so that math-heavy epilogues (erf-GELU, RoPE) stay hidden under
+// short-K mainloops (ViT K = 1024 / 1152).
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2) computes a 256 x BN tile with
 // tcgen05.mma.cta_group::2; each CTA stages its own 128 rows of A and half of the W tile, which halves the
 // shared-memory / L2 traffic per flop.
@@ -49,7 +51,8 @@ struct GemmShape {
   int group_m;  // rasterisation group size (row-tiles)
 };
 
-static constexpr int kGemmThreads = 256;
+static constexpr int kGemmThreads = 384;
+static constexpr int kEpiWarps = 8;
 static constexpr int kBM = 128;           // rows per CTA
 static constexpr int kStageABytes = kBM * 128;
 
@@ -115,7 +118,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+      mbar_init(&tmem_empty[a], kEpiWarps * CG);  // one arrive per epilogue warp of every CTA in the group
     }
     fence_barrier_init();
   }
@@ -189,7 +192,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int part = (warp - 4) >> 2;   // which half of the column chunks this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = worker; t < num_tiles; t += num_workers) {
@@ -206,7 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
         const __nv_bfloat16* res = epi.resid ? epi.resid + static_cast<long long>(row) * epi.ldr : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = part; c < BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -269,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
         const int n_out = shape.N / 2;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = part; c < BN / 64; c += 2) {
           uint32_t g[32], u[32];
           tmem_ld32(taddr + c * 64, g);
           tmem_ld32(taddr + c * 64 + 32, u);
@@ -305,12 +309,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int Dm = epi.H * 128;
         __nv_bfloat16* qrow = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
 #pragma unroll 1
-        for (int hh = 0; hh < BN / 128; ++hh) {
+        for (int idx = part; idx < BN / 64; idx += 2) {  // (head, half) pairs of this tile
+          const int hh = idx >> 1, half = idx & 1;
           const int colh = col0 + hh * 128;
           const int which = colh / Dm, h = (colh - which * Dm) >> 7;
           const long long coff = ((static_cast<long long>(bidx) * epi.H + h) * epi.Tmax + pos) * 128;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          {
             uint32_t lo[32], hi[32];
             tmem_ld32(taddr + hh * 128 + half * 32, lo);
             tmem_ld32(taddr + hh * 128 + 64 + half * 32, hi);
@@ -357,7 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else {  // kModeF32
         float* out = reinterpret_cast<float*>(epi.out) + static_cast<long long>(row) * epi.ldo;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = part; c < BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
