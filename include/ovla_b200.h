@@ -94,6 +94,11 @@ int ovla_detokenize(const long long* ids_dev, int n, int action_dim, int vocab_s
 int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K, int T,
                        int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev, long long ldo,
                        void* k_cache_dev, void* v_cache_dev, int Tmax, int tile_n, int cta_group, void* stream);
+/* PrismaticImageProcessor.apply_transform (processing_prismatic.py:128-145) for frames already at model resolution +
+ * the bf16 cast of get_vla_action (openvla_utils.py:186): uint8 HWC [B,S,S,3] -> bf16 [B, 3*n_towers, S, S];
+ * mean/std: fp32 [n_towers*3] on the device.  Bit-identical to torchvision's to_tensor + normalize on the host. */
+int ovla_preprocess_frames(const void* frames_u8_dev, int B, int S, int n_towers, const float* mean_dev,
+                           const float* std_dev, void* pixel_values_out_dev, void* stream);
 /* small-batch (M <= 8) weight-streaming GEMM with the same epilogues as ovla_gemm */
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream);
@@ -176,6 +181,12 @@ int ovla_probe_gather_labels(const signed char* y_dev, long long ldy, const long
 int ovla_probe_bce_grad(const float* z_dev, long long ldz, const signed char* yp_dev, int n, int K, int Kpad,
                         int kind0, int heads, const float* pos_weight_dev, float pos_weight_scalar, float* dzt_dev,
                         long long ldt, float* stats_dev, void* stream);
+/* Direct 3-class probe (train_3class_direct.py:147-212): z fp32 [n, 3K] viewed as [n*K, 3], class-weighted CE over
+ * {-1 -> 0, 0 -> 1, 1 -> 2}; UN-normalised gradient transposed into dzt [rows_pad >= 3K, n]; stats[0] += sum w*nll,
+ * stats[1] += sum w (the weighted-mean normaliser).  class_w3_host: 3 floats on the HOST.                      */
+int ovla_probe_ce3_grad(const float* z_dev, long long ldz, const signed char* yp_dev, long long ldy, int n, int K,
+                        int rows_pad, const float* class_w3_host, float* dzt_dev, long long ldt, float* stats_dev,
+                        void* stream);
 /* out[r] = sum_c a[r, c]  (bias gradient from dzt) */
 int ovla_probe_rowsum(const float* a_dev, long long lda, int rows, int cols, float* out_dev, void* stream);
 /* torch.optim.AdamW step on the flat [W (rows x D) | b (rows)] buffer; gradient rows of head h are divided by

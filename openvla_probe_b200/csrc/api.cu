@@ -133,6 +133,12 @@ int ovla_detokenize(const long long* ids, int n, int action_dim, int vocab_size,
 }
 
 
+int ovla_preprocess_frames(const void* frames_u8_dev, int B, int S, int n_towers, const float* mean_dev,
+                           const float* std_dev, void* pixel_values_out_dev, void* stream) {
+  return preprocess_frames_launch(frames_u8_dev, B, S, n_towers, mean_dev, std_dev, pixel_values_out_dev,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int ovla_probe_gather(const float* x, long long ldx, const long long* perm, int n, int D, float* xp, long long ldp,
                       float* xpt, long long ldt, void* stream) {
   return probe_gather_launch(x, ldx, perm, n, D, xp, ldp, xpt, ldt, static_cast<cudaStream_t>(stream));
@@ -145,6 +151,11 @@ int ovla_probe_bce_grad(const float* z, long long ldz, const signed char* y, int
                         int heads, const float* pos_weight, float pos_weight_scalar, float* dzt, long long ldt,
                         float* stats, void* stream) {
   return probe_bce_grad_launch(z, ldz, y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar, dzt, ldt, stats,
+                               static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_ce3_grad(const float* z, long long ldz, const signed char* y, long long ldy, int n, int K, int rows_pad,
+                        const float* class_w3_host, float* dzt, long long ldt, float* stats, void* stream) {
+  return probe_ce3_grad_launch(z, ldz, y, ldy, n, K, rows_pad, class_w3_host, dzt, ldt, stats,
                                static_cast<cudaStream_t>(stream));
 }
 int ovla_probe_rowsum(const float* a, long long lda, int rows, int cols, float* out, void* stream) {

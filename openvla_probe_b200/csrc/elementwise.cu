@@ -377,3 +377,44 @@ int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_s
 }
 
 }  // namespace ovla
+
+namespace ovla {
+
+// ------------------------------------------------------------------------------------------- frame pre-processing
+// PrismaticImageProcessor.apply_transform for frames that already have the model resolution
+// (processing_prismatic.py:128-145: to_tensor -> normalize per tower -> channel-stack) followed by the bf16 cast of
+// get_vla_action (openvla_utils.py:186):  out[b, 3*tw + c, y, x] = bf16((float(u8[b, y, x, c]) / 255 - mean[tw][c]) / std[tw][c])
+// with IEEE fp32 divisions, so the result is bit-identical to torchvision on the host.
+__global__ void preprocess_frames_kernel(const unsigned char* __restrict__ frames, int S, int n_towers,
+                                         const float* __restrict__ mean, const float* __restrict__ stdv,
+                                         __nv_bfloat16* __restrict__ out, long long n_pix) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
+  if (idx >= n_pix) return;
+  const long long b = idx / (static_cast<long long>(S) * S);
+  const long long yx = idx - b * S * S;
+  const unsigned char* p = frames + idx * 3;
+  const float v[3] = {__fdiv_rn(static_cast<float>(p[0]), 255.f), __fdiv_rn(static_cast<float>(p[1]), 255.f),
+                      __fdiv_rn(static_cast<float>(p[2]), 255.f)};
+  for (int tw = 0; tw < n_towers; ++tw) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float r = __fdiv_rn(__fsub_rn(v[c], mean[tw * 3 + c]), stdv[tw * 3 + c]);
+      out[(b * 3 * n_towers + tw * 3 + c) * S * S + yx] = __float2bfloat16_rn(r);
+    }
+  }
+}
+
+int preprocess_frames_launch(const void* frames_u8, int B, int S, int n_towers, const float* mean, const float* stdv,
+                             void* out, cudaStream_t st) {
+  const long long n_pix = static_cast<long long>(B) * S * S;
+  if (n_pix <= 0) return 0;
+  if (n_towers < 1 || n_towers > 2) return set_error("preprocess: n_towers must be 1 or 2");
+  ProfScope prof(kCatOther, 0.0, n_pix * (3.0 + 6.0 * n_towers), st);
+  preprocess_frames_kernel<<<static_cast<unsigned>((n_pix + 255) / 256), 256, 0, st>>>(
+      static_cast<const unsigned char*>(frames_u8), S, n_towers, mean, stdv, static_cast<__nv_bfloat16*>(out), n_pix);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace ovla

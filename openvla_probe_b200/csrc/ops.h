@@ -51,6 +51,8 @@ int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_s
                         int n_centers, const double* q01, const double* q99, const unsigned char* mask, double* out,
                         cudaStream_t st);
 
+int preprocess_frames_launch(const void* frames_u8, int B, int S, int n_towers, const float* mean, const float* stdv,
+                             void* out, cudaStream_t st);
 
 // probe.cu
 int probe_gather_launch(const float* X, long long ldx, const long long* perm, int n, int D, float* Xp, long long ldp,
@@ -64,5 +66,10 @@ int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float
 int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
                        long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
                        int step, cudaStream_t st);
+
+// probe3.cu
+int probe_ce3_grad_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, int n, int K,
+                          int rows_pad, const float* class_w3_host, float* dZT, long long ldt, float* stats,
+                          cudaStream_t st);
 
 }  // namespace ovla

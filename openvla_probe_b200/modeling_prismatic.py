@@ -157,6 +157,36 @@ class OpenVLAForActionPrediction:
             self._pin[key] = t
         return t[:n].view(*shape)
 
+    # ------------------------------------------------------------------ frames -> pixel_values on the device
+    _TOWER_STATS = {  # timm data configs consumed at convert_openvla_weights_to_hf.py:193-197
+        "dino": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+        "siglip": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+    }
+
+    @torch.no_grad()
+    def preprocess_frames(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """uint8 HWC frames [B, S, S, 3] already at model resolution -> bf16 `pixel_values` [B, 3*towers, S, S] on the
+        device: `PrismaticImageProcessor.apply_transform` (to_tensor + per-tower normalize, processing_prismatic.py:128-145)
+        plus the bf16 cast of openvla_utils.py:186, bit-identical to the host path.  Only the uint8 bytes cross PCIe."""
+        import ctypes as C
+
+        c = self.config
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or tuple(frames_u8.shape[1:]) != (c.image_size, c.image_size, 3):
+            raise ValueError(f"frames must be uint8 [B, {c.image_size}, {c.image_size}, 3] (resize / crop are host-side input prep)")
+        names = ["dino", "siglip"] if c.use_fused_vision_backbone else ["siglip"]
+        if not hasattr(self, "_norm_dev"):
+            mean = torch.tensor([v for n in names for v in self._TOWER_STATS[n][0]], dtype=torch.float32)
+            std = torch.tensor([v for n in names for v in self._TOWER_STATS[n][1]], dtype=torch.float32)
+            self._norm_dev = (mean.to(self.device), std.to(self.device))
+        fr = frames_u8.to(self.device, non_blocking=True).contiguous()
+        B = fr.shape[0]
+        out = torch.empty(B, 3 * len(names), c.image_size, c.image_size, dtype=torch.bfloat16, device=self.device)
+        if B:
+            _lib.check(self.engine.lib.ovla_preprocess_frames(
+                C.c_void_p(fr.data_ptr()), B, c.image_size, len(names), C.c_void_p(self._norm_dev[0].data_ptr()),
+                C.c_void_p(self._norm_dev[1].data_ptr()), C.c_void_p(out.data_ptr()), _lib.stream_ptr()))
+        return out
+
     # ------------------------------------------------------------------ public surface
     @torch.no_grad()
     def predict_action(self, input_ids: Optional[torch.Tensor] = None, unnorm_key: Optional[str] = None,

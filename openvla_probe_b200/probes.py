@@ -35,7 +35,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-KIND_OBJECT, KIND_SPATIAL, KIND_DUAL = "object", "spatial", "dual"
+KIND_OBJECT, KIND_SPATIAL, KIND_DUAL, KIND_3CLASS = "object", "spatial", "dual", "3class"
 _KIND0 = {KIND_OBJECT: 0, KIND_SPATIAL: 1, KIND_DUAL: 2}
 
 
@@ -172,6 +172,29 @@ def prepare_dual(cache: Dict[int, dict], seed: int = 0) -> ProbeSplit:
     return ProbeSplit(train_ids, val_ids, keep, pw, Y_tr.shape[1])
 
 
+def prepare_3class(cache: Dict[int, dict], seed: int = 0) -> ProbeSplit:
+    """train_3class_direct.py:82-131: same 1 %-99 % keep rule as the dual-head script; inverse-frequency class weights
+    for {N/A, False, True} over the kept TRAIN labels, normalised to sum to 3 (`pos_weight` holds the 3 weights)."""
+    train_ids, val_ids = split_episodes(cache, seed)
+    Y_tr = _stack_labels(cache, train_ids)
+    m = Y_tr != -1
+    cnt = m.sum(0)
+    freq = torch.full((Y_tr.shape[1],), -1.0)
+    ok = cnt > 0
+    freq[ok] = ((Y_tr == 1) & m).sum(0)[ok].float() / cnt[ok]
+    keep = ((freq > 0.01) & (freq < 0.99)).nonzero(as_tuple=True)[0]
+    if len(keep) == 0:
+        keep = torch.arange(Y_tr.shape[1])
+    Yk = Y_tr[:, keep]
+    total = Yk.numel()
+    if total == 0:
+        w = torch.ones(3)
+    else:
+        w = torch.tensor([total / (3 * (float((Yk == v).sum()) + 1e-6)) for v in (-1, 0, 1)], dtype=torch.float32)
+        w = w / w.sum() * 3
+    return ProbeSplit(train_ids, val_ids, keep, w, Y_tr.shape[1])
+
+
 def layer_matrix(cache: Dict[int, dict], ids: Sequence[int], layer: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """The samples StepDS enumerates (train_object_probes.py:129-145), as dense tensors: X fp32 [N, D], Y int8 [N, L]."""
     xs, ys = [], []
@@ -238,8 +261,10 @@ class ProbeTrainer:
             raise ValueError("feature dim must be a multiple of 4")
         self.kind, self.D, self.K = kind, D, K
         self.heads = 2 if kind == KIND_DUAL else 1
-        self.Kpad = (K + 7) // 8 * 8
-        self.rows = self.heads * self.Kpad
+        self.Kpad = (K + 7) // 8 * 8                      # label columns of the gathered int8 label matrix
+        self.n_out = 3 * K if kind == KIND_3CLASS else K  # real output rows per head
+        self.rows_per_head = (3 * K + 7) // 8 * 8 if kind == KIND_3CLASS else self.Kpad
+        self.rows = self.heads * self.rows_per_head
         self.batch, self.lr, self.wd = batch, lr, weight_decay
         self.dev = torch.device("cuda", device)
         self.group = group
@@ -254,7 +279,11 @@ class ProbeTrainer:
         self.M = torch.zeros_like(self.P)
         self.V = torch.zeros_like(self.P)
         self.step_count = 0
-        if kind == KIND_DUAL:
+        self.class_w = None
+        if kind == KIND_3CLASS:
+            self.pw_vec, self.pw_scalar = None, 1.0
+            self.class_w = (C.c_float * 3)(*[float(v) for v in pos_weight])
+        elif kind == KIND_DUAL:
             self.pw_vec, self.pw_scalar = None, float(pos_weight)
         else:
             pw = torch.ones(self.Kpad, dtype=torch.float32)
@@ -272,19 +301,19 @@ class ProbeTrainer:
         names = ["presence_head", "truth_head"] if self.heads == 2 else [None]
         for h, nm in enumerate(names):
             if init_state is None:
-                lin = torch.nn.Linear(self.D, self.K)
+                lin = torch.nn.Linear(self.D, self.n_out)
                 w0, b0 = lin.weight.detach(), lin.bias.detach()
             else:
                 pre = f"{nm}." if nm else ""
                 w0, b0 = init_state[pre + "weight"].float(), init_state[pre + "bias"].float()
-            W[h * self.Kpad: h * self.Kpad + self.K].copy_(w0)
-            b[h * self.Kpad: h * self.Kpad + self.K].copy_(b0)
+            W[h * self.rows_per_head: h * self.rows_per_head + self.n_out].copy_(w0)
+            b[h * self.rows_per_head: h * self.rows_per_head + self.n_out].copy_(b0)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         W = self.P[: self.n_w].view(self.rows, self.D)
         b = self.P[self.n_w:]
         if self.heads == 1:
-            return {"weight": W[: self.K].cpu().clone(), "bias": b[: self.K].cpu().clone()}
+            return {"weight": W[: self.n_out].cpu().clone(), "bias": b[: self.n_out].cpu().clone()}
         return {"presence_head.weight": W[: self.K].cpu().clone(), "presence_head.bias": b[: self.K].cpu().clone(),
                 "truth_head.weight": W[self.Kpad: self.Kpad + self.K].cpu().clone(),
                 "truth_head.bias": b[self.Kpad: self.Kpad + self.K].cpu().clone()}
@@ -350,12 +379,18 @@ class ProbeTrainer:
             xp = self.Xp.data_ptr() + lo * self.D * 4
             self._gemm_tf32(xp, self.D, self.P.data_ptr(), self.D, n, self.rows, self.D, self.Z.data_ptr(), self.rows,
                             bias=self.P[self.n_w:])
-            ck(self.lib.ovla_probe_bce_grad(C.c_void_p(self.Z.data_ptr()), C.c_longlong(self.rows),
-                                            C.c_void_p(self.Yp.data_ptr() + lo * self.Kpad), n, self.K, self.Kpad,
-                                            _KIND0[self.kind], self.heads,
-                                            C.c_void_p(self.pw_vec.data_ptr()) if self.pw_vec is not None else None,
-                                            C.c_float(self.pw_scalar), C.c_void_p(self.dZT.data_ptr()),
-                                            C.c_longlong(self.ldz_t), C.c_void_p(stats.data_ptr()), st))
+            if self.kind == KIND_3CLASS:
+                ck(self.lib.ovla_probe_ce3_grad(C.c_void_p(self.Z.data_ptr()), C.c_longlong(self.rows),
+                                                C.c_void_p(self.Yp.data_ptr() + lo * self.Kpad), C.c_longlong(self.Kpad), n,
+                                                self.K, self.rows, self.class_w, C.c_void_p(self.dZT.data_ptr()),
+                                                C.c_longlong(self.ldz_t), C.c_void_p(stats.data_ptr()), st))
+            else:
+                ck(self.lib.ovla_probe_bce_grad(C.c_void_p(self.Z.data_ptr()), C.c_longlong(self.rows),
+                                                C.c_void_p(self.Yp.data_ptr() + lo * self.Kpad), n, self.K, self.Kpad,
+                                                _KIND0[self.kind], self.heads,
+                                                C.c_void_p(self.pw_vec.data_ptr()) if self.pw_vec is not None else None,
+                                                C.c_float(self.pw_scalar), C.c_void_p(self.dZT.data_ptr()),
+                                                C.c_longlong(self.ldz_t), C.c_void_p(stats.data_ptr()), st))
             ck(self.lib.ovla_probe_rowsum(C.c_void_p(self.dZT.data_ptr()), C.c_longlong(self.ldz_t), self.rows, n,
                                           C.c_void_p(self.G.data_ptr() + self.n_w * 4), st))
             # dW[rows, D] = dZT[rows, n] . (XpT[:, lo:hi])^T      (contraction over the local batch)
@@ -365,7 +400,7 @@ class ProbeTrainer:
         self.step_count += 1
         ck(self.lib.ovla_probe_adamw(C.c_void_p(self.P.data_ptr()), C.c_void_p(self.G.data_ptr()),
                                      C.c_void_p(self.M.data_ptr()), C.c_void_p(self.V.data_ptr()),
-                                     C.c_longlong(self.n_w), self.D, self.Kpad, C.c_longlong(self.n_total),
+                                     C.c_longlong(self.n_w), self.D, self.rows_per_head, C.c_longlong(self.n_total),
                                      C.c_void_p(stats.data_ptr()), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999),
                                      C.c_float(1e-8), C.c_float(self.wd), self.step_count, st))
 
@@ -401,6 +436,12 @@ def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor,
     Z = trainer.logits(X.to(trainer.dev, torch.float32).contiguous()).cpu()
     y = Y[:, keep].long().cpu()
     K, Kp = trainer.K, trainer.Kpad
+    if kind == KIND_3CLASS:                       # train_3class_direct.py:196-207: argmax over the 3 logits of each label
+        tgt = (y + 1).view(-1)
+        pred = Z[:, :3 * K].reshape(-1, 3).argmax(1)
+        acc = float((pred == tgt).float().mean()) if tgt.numel() else 0.0
+        f1 = f1_score(tgt.numpy(), pred.numpy(), labels=[0, 1, 2], average="macro", zero_division=0) if tgt.numel() else 0.0
+        return dict(val_acc=acc, val_f1=f1)
     if kind == KIND_DUAL:
         pres_t, truth_t, mask = (y != -1).long(), (y == 1).long(), (y != -1)
         pres_p = (Z[:, :K].sigmoid() > 0.5).long()
@@ -433,8 +474,9 @@ def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 2
     import pandas as pd
 
     cache = load_episodes(log_dir, exclude)
-    split = {KIND_OBJECT: prepare_object, KIND_SPATIAL: prepare_spatial, KIND_DUAL: prepare_dual}[kind](cache)
-    if kind == KIND_DUAL:
+    split = {KIND_OBJECT: prepare_object, KIND_SPATIAL: prepare_spatial, KIND_DUAL: prepare_dual,
+             KIND_3CLASS: prepare_3class}[kind](cache)
+    if kind in (KIND_DUAL, KIND_3CLASS):
         torch.manual_seed(seed)
     records = []
     rank0 = True
@@ -446,12 +488,18 @@ def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 2
             continue
         tr = ProbeTrainer(kind, Xtr.shape[1], len(split.keep), split.pos_weight, batch=batch, device=device, group=group)
         rank0 = tr.rank == 0
-        tr.fit(Xtr, Ytr, split.keep, epochs, seed=seed + L, drop_last=(kind == KIND_DUAL))
+        tr.fit(Xtr, Ytr, split.keep, epochs, seed=seed + L, drop_last=(kind in (KIND_DUAL, KIND_3CLASS)))
         rec = dict(layer=L, **evaluate(kind, tr, Xva, Yva, split.keep))
         records.append(rec)
         if rank0:
             os.makedirs(out_dir, exist_ok=True)
-            if kind == KIND_DUAL:
+            if kind == KIND_3CLASS:
+                torch.save({"model_type": "Direct3ClassProbe", "state_dict": tr.state_dict(), "layer": L,
+                            "kept_indices": split.keep.tolist(), "input_dim": tr.D, "num_output_labels_probed": tr.K,
+                            "num_classes_per_label": 3, "class_weights_used": [float(v) for v in split.pos_weight],
+                            "class_mapping": {"NA(-1)": 0, "False(0)": 1, "True(1)": 2}},
+                           os.path.join(out_dir, f"linear_probe_3class_direct_L{L:02d}.pth"))
+            elif kind == KIND_DUAL:
                 torch.save({"model_type": "DualHeadProbe", "state_dict": tr.state_dict(), "layer": L,
                             "kept_indices": split.keep.tolist(), "input_dim": tr.D, "num_output_labels": tr.K,
                             "presence_pos_weight_used": float(split.pos_weight)},
@@ -463,14 +511,14 @@ def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 2
                 print(f"L{L:02d}  " + "  ".join(f"{k}={v:.3f}" for k, v in rec.items() if k != "layer"))
     if rank0:
         name = {KIND_OBJECT: "probe_metrics_object.csv", KIND_SPATIAL: "probe_metrics_spatial.csv",
-                KIND_DUAL: "probe_metrics_dual_head_final.csv"}[kind]
+                KIND_DUAL: "probe_metrics_dual_head_final.csv", KIND_3CLASS: "probe_metrics_3class_direct.csv"}[kind]
         pd.DataFrame(records).to_csv(os.path.join(out_dir, name), index=False)
     return records
 
 
 def main():
     cli = argparse.ArgumentParser(description="B200-native probe training (object / spatial / dual-head)")
-    cli.add_argument("--kind", default=KIND_OBJECT, choices=[KIND_OBJECT, KIND_SPATIAL, KIND_DUAL])
+    cli.add_argument("--kind", default=KIND_OBJECT, choices=[KIND_OBJECT, KIND_SPATIAL, KIND_DUAL, KIND_3CLASS])
     cli.add_argument("--log_dir", default="experiments/logs", help="folder containing episode_*.pt")
     cli.add_argument("--epochs", type=int, default=20)
     cli.add_argument("--batch", type=int, default=4096)

@@ -306,3 +306,30 @@ def test_fused_qkv_rope_gemm_equals_unfused_path(L, B, T, H, bn, cg):
     assert torch.equal(kc1, kc0) and torch.equal(vc1, vc0)
     assert lib.ovla_qkv_rope_gemm(P(x), C.c_longlong(K), P(W), C.c_longlong(K), B * T, H, K, T, 20, P(cd), P(sd), P(out),
                                   C.c_longlong(3 * D), P(kc1), P(vc1), Tmax, bn, cg, None) != 0      # past KV capacity
+
+
+def test_preprocess_frames_bit_exact_and_native_twin():
+    """uint8 frames -> bf16 pixel_values on the device == the host transform (to_tensor, per-tower normalize, bf16 cast),
+    bit for bit; the native-style OpenVLA.predict_action(image, instruction) gives the same action as the HF surface."""
+    import dataclasses
+
+    from openvla_probe_b200 import config as cfgmod
+    from openvla_probe_b200.modeling_prismatic import from_state_dict
+    from openvla_probe_b200.vlas import OpenVLA, PurePromptBuilder, hash_tokenizer
+
+    od = O.tiny_dims()
+    cfg = dataclasses.replace(cfgmod.tiny(), norm_stats={"synthetic": {"action": O.default_stats()}})
+    model = from_state_dict(cfg, O.make_weights(od, seed=0), max_batch=2, max_prompt_len=40)
+    rng = np.random.default_rng(1)                      # same frames as O.make_inputs(seed=1)
+    img = rng.integers(0, 256, (2, od.image_size, od.image_size, 3), dtype=np.uint8)
+    _, px_host = O.make_inputs(od, 2, prompt_len=9, seed=1)
+    px_dev = model.preprocess_frames(torch.from_numpy(img))
+    assert torch.equal(px_dev.cpu(), px_host)
+    pb = PurePromptBuilder()
+    pb.add_turn("human", "What action should the robot take to pick up the cup?")
+    assert pb.get_prompt() == "In: What action should the robot take to pick up the cup?\nOut:"
+    vla = OpenVLA(model)
+    a_native = vla.predict_action(img[0], "Pick up the cup", unnorm_key="synthetic")
+    ids = torch.tensor([hash_tokenizer(pb.get_prompt())])
+    a_hf = model.predict_action(ids, unnorm_key="synthetic", pixel_values=px_host[:1])
+    assert a_native.shape == (7,) and np.array_equal(a_native, a_hf)

@@ -185,3 +185,41 @@ def test_episode_round_trip_and_training_loop(tmp_path):
     ck = torch.load(str(tmp_path / "out" / "linear_probe_dual_head_final_L01.pth"), weights_only=False)
     assert ck["model_type"] == "DualHeadProbe" and "presence_head.weight" in ck["state_dict"]
     assert recs[0]["truth_acc_va"] > 0.72
+
+
+def test_3class_probe_steps_vs_autograd():
+    """Direct 3-class probe (train_3class_direct.py:147-212): weighted CrossEntropy over [B*K, 3] logits."""
+    from openvla_probe_b200.probes import ProbeTrainer
+
+    X, Y, keep = _data(N=520, D=128, L=21)
+    K, D = len(keep), X.shape[1]
+    cw = torch.tensor([0.6, 1.1, 1.3])
+    torch.manual_seed(4)
+    tr = ProbeTrainer("3class", D, K, cw, batch=256)
+    sd0 = tr.state_dict()
+    assert sd0["weight"].shape == (3 * K, D)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-3, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss(weight=cw)
+    perm = torch.randperm(X.shape[0], generator=torch.Generator().manual_seed(9))
+    tr.load_epoch(X.cuda(), Y.cuda(), keep, perm, drop_last=True)
+    assert len(tr.steps) == 2
+    for s in range(2):
+        idx = perm[s * 256: (s + 1) * 256]
+        Xb, Yb = X[idx], Y[idx][:, keep].long()
+        z = Xb @ params["weight"].t() + params["bias"]
+        loss = crit(z.view(-1, 3), (Yb + 1).view(-1))
+        opt.zero_grad()
+        loss.backward()
+        tr.train_step(s)
+        assert abs(tr.step_loss() - float(loss.detach())) <= 1e-3 * float(loss.detach()) + 1e-5
+        G = tr.G.cpu()
+        cnt = G[tr.n_total + 1]
+        dW = G[: tr.n_w].view(tr.rows, D)[: 3 * K] / cnt
+        db = G[tr.n_w: tr.n_w + 3 * K] / cnt
+        assert (dW - params["weight"].grad).norm() / params["weight"].grad.norm() < 2e-3
+        assert (db - params["bias"].grad).norm() / params["bias"].grad.norm() < 2e-3
+        opt.step()
+        for k, v in tr.state_dict().items():
+            moved = (params[k].detach() - sd0[k]).norm()
+            assert (v - params[k].detach()).norm() <= 0.05 * moved + 1e-6, k
