@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_rope_attn_kernel(
   __nv_bfloat16* vb = vc + head_off;
   const __nv_bfloat16* row = qkv + b * qkv_ld + h * HD;
   const long long D = static_cast<long long>(H) * HD;
-  // let a PDL-launched successor (the o_proj GEMV) start prefetching its weights while this kernel runs
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // let a PDL-launched successor (the o_proj GEMV) start prefetching its weights while this kernel runs, then wait
+  // for the QKV projection this kernel consumes
+  griddep_launch_dependents();
+  griddep_wait();
 
   // ---- RoPE on q and k (pairs i, i + HD/2), append k and v at `pos`
   if (tid < HD / 2) {
@@ -153,11 +155,11 @@ int decode_rope_attn_launch(const void* qkv, long long qkv_ld, const void* cos_t
   if (smem > 48 * 1024) return set_error("decode attention: ctx=%d too long", ctx);
   dim3 grid(H, B);
   ProfScope prof(kCatDecodeAttn, 4.0 * B * H * ctx * head_dim, 4.0 * B * H * ctx * head_dim + 12.0 * B * H * head_dim, st);
-  decode_rope_attn_kernel<128><<<grid, kDecThreads, smem, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), qkv_ld, static_cast<const __nv_bfloat16*>(cos_t),
-      static_cast<const __nv_bfloat16*>(sin_t), pos, static_cast<__nv_bfloat16*>(kc), static_cast<__nv_bfloat16*>(vc),
-      Tmax, static_cast<__nv_bfloat16*>(out), o_ld, 1.0f / sqrtf(static_cast<float>(head_dim)));
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(decode_rope_attn_kernel<128>, grid, dim3(kDecThreads), smem, st,
+                      static_cast<const __nv_bfloat16*>(qkv), qkv_ld, static_cast<const __nv_bfloat16*>(cos_t),
+                      static_cast<const __nv_bfloat16*>(sin_t), pos, static_cast<__nv_bfloat16*>(kc),
+                      static_cast<__nv_bfloat16*>(vc), Tmax, static_cast<__nv_bfloat16*>(out), o_ld,
+                      1.0f / sqrtf(static_cast<float>(head_dim))));
   count_launch();
   return 0;
 }

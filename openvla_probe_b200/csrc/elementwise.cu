@@ -122,6 +122,8 @@ int copy_rows_launch(const void* src, long long src_batch, long long src_ld, int
 __global__ void embed_splice_kernel(const long long* __restrict__ ids, int P, const __nv_bfloat16* __restrict__ E,
                                     int vocab, const __nv_bfloat16* __restrict__ proj, int np, int D,
                                     __nv_bfloat16* __restrict__ x, long long total_vec, int* __restrict__ err) {
+  griddep_launch_dependents();
+  griddep_wait();  // the ids may come from the argmax of the previous decode step
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total_vec) return;
   const int dv = D / 8;
@@ -148,10 +150,9 @@ int embed_splice_launch(const void* ids, int B, int P, const void* E, int vocab,
                         void* x, int* err_flag, cudaStream_t st) {
   const long long total = static_cast<long long>(B) * (np + P) * (D / 8);
   if (total <= 0) return 0;
-  embed_splice_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      static_cast<const long long*>(ids), P, static_cast<const __nv_bfloat16*>(E), vocab,
-      static_cast<const __nv_bfloat16*>(proj), np, D, static_cast<__nv_bfloat16*>(x), total, err_flag);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(embed_splice_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st,
+                      static_cast<const long long*>(ids), P, static_cast<const __nv_bfloat16*>(E), vocab,
+                      static_cast<const __nv_bfloat16*>(proj), np, D, static_cast<__nv_bfloat16*>(x), total, err_flag));
   count_launch();
   return 0;
 }
@@ -304,6 +305,8 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
                                                           long long* __restrict__ out) {
   __shared__ float sv[8];
   __shared__ int si[8];
+  griddep_launch_dependents();
+  griddep_wait();
   const float* row = x + blockIdx.x * ld;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
@@ -336,8 +339,7 @@ int argmax_launch(const float* x, long long ld, int rows, int n, long long* out,
   if (rows <= 0) return 0;
   if (n <= 0) return set_error("argmax: empty rows");
   if (ld % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return set_error("argmax: rows must be 16-byte aligned");
-  argmax_rows_kernel<<<rows, 256, 0, st>>>(x, ld, n, out);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(argmax_rows_kernel, dim3(rows), dim3(256), 0, st, x, ld, n, out));
   count_launch();
   return 0;
 }

@@ -18,9 +18,6 @@ namespace ovla {
 
 static constexpr int kGemvThreadsDefault = 128;
 
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -162,7 +159,7 @@ static int gemv_launch_t(const __nv_bfloat16* X, long long ldx, const __nv_bfloa
   attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = (use_pdl() && pdl_enabled()) ? 1 : 0;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, gemv_kernel<MB, MODE, kCh>, X, ldx, Wp, ldw, M, N, K, epi));
   count_launch();
   return 0;

@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -43,6 +44,15 @@ cudaEvent_t get_event() {
   return e;
 }
 }  // namespace
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OVLA_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void prof_enable(bool on) { g_prof_on = on; }
 bool prof_enabled() { return g_prof_on; }

@@ -33,6 +33,26 @@ struct ProfScope {
   }
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl may begin while its stream predecessor
+// is still draining; such kernels call griddep_wait() (ptx.cuh) before touching anything the predecessor wrote.
+// OVLA_PDL=0 disables the attribute (plain stream serialisation) for A/B measurements.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

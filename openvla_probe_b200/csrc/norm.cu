@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(128) norm_rows_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ b, float eps,
                                                         __nv_bfloat16* __restrict__ out, long long ldo, int rows,
                                                         int D) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -105,8 +107,7 @@ static int norm_dispatch(const void* x, long long ldx, const void* w, const void
   auto O = static_cast<__nv_bfloat16*>(out);
 #define OVLA_NORM_CASE(C)                                                                        \
   if (chunks <= C) {                                                                             \
-    norm_rows_kernel<MODE, C><<<grid, block, 0, st>>>(X, ldx, W, B, eps, O, ldo, rows, D);       \
-    CUDA_TRY(cudaGetLastError());                                                                \
+    CUDA_TRY(launch_pdl(norm_rows_kernel<MODE, C>, grid, block, 0, st, X, ldx, W, B, eps, O, ldo, rows, D)); \
     count_launch();                                                                              \
     return 0;                                                                                    \
   }

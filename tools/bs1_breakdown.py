@@ -47,3 +47,15 @@ for i, nm in enumerate(names):
     tot += ms[i]
     print(f"{nm:14s} launches={n[i]:5d} ms={ms[i]:8.3f} TF/s={fl[i] / max(ms[i], 1e-9) / 1e9:8.1f} GB/s={by[i] / max(ms[i], 1e-9) / 1e6:8.1f}")
 print("sum of kernel ms:", tot)
+
+# phase split in graph mode: prefill only (n_new=0), +lm_head/argmax (n_new=1), full (n_new=7)
+for n_new in (0, 1, 7):
+    for _ in range(3):
+        model.engine.run(ids, px, pool_len, 0, n_new)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); model.engine.run(ids, px, pool_len, 0, n_new); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print(f"n_new={n_new}: p50 {sorted(ts)[5]:.2f} ms")
