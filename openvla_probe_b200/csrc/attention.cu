@@ -52,8 +52,10 @@ struct AttnStrides {
 };
 
 // HD: real head dim; HDP: head dim padded to a multiple of 16 (zero-filled in smem)
-template <int HD, int HDP, bool CAUSAL, int BR>
-__global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q,
+// LITE: single-buffered K/V tiles + Q fragments re-read from shared memory: 52 KB and <= 128 registers per 64-row
+// CTA at head_dim 128, so four CTAs (16 warps) share an SM and hide each other's softmax / load phases.
+template <int HD, int HDP, bool CAUSAL, int BR, bool LITE>
+__global__ void __launch_bounds__(BR * 2, LITE ? 4 : 1) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q,
                                                          const __nv_bfloat16* __restrict__ K,
                                                          const __nv_bfloat16* __restrict__ V,
                                                          __nv_bfloat16* __restrict__ O, AttnStrides st, int Tq, int Tk,
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
   constexpr int NTHR = BR * 2;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);  // [BR][LD]
   __nv_bfloat16* sK = sQ + BR * LD;                                  // [2][64][LD]
-  __nv_bfloat16* sV = sK + 2 * 64 * LD;                              // [2][64][LD]
+  constexpr int NBUF = LITE ? 1 : 2;
+  __nv_bfloat16* sV = sK + NBUF * 64 * LD;                           // [NBUF][64][LD]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BR, h = blockIdx.y, b = blockIdx.z;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
   load_tile(sV, Vb, st.v_t, 0, Tk, 64);
   cp_async_commit();
 
-  uint32_t qf[KS][4];
+  uint32_t qf[LITE ? 1 : KS][4];  // LITE re-reads the Q fragments from shared memory instead of pinning 32 registers
   float o_acc[NT][4];
 #pragma unroll
   for (int n = 0; n < NT; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
@@ -102,8 +105,15 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
   const int qrow0 = q0 + warp * 16 + g;  // this thread's two query rows: qrow0, qrow0 + 8
 
   for (int kt = 0; kt < n_kt; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < n_kt) {
+    const int buf = LITE ? 0 : (kt & 1);
+    if (LITE) {
+      if (kt > 0) {  // the barrier that ended the previous iteration freed the single buffer
+        load_tile(sK, Kb, st.k_t, kt * 64, Tk, 64);
+        load_tile(sV, Vb, st.v_t, kt * 64, Tk, 64);
+        cp_async_commit();
+      }
+      cp_async_wait<0>();
+    } else if (kt + 1 < n_kt) {
       load_tile(sK + (buf ^ 1) * 64 * LD, Kb, st.k_t, (kt + 1) * 64, Tk, 64);
       load_tile(sV + (buf ^ 1) * 64 * LD, Vb, st.v_t, (kt + 1) * 64, Tk, 64);
       cp_async_commit();
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (kt == 0) {
+    if (!LITE && kt == 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
@@ -131,14 +141,20 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
       for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
   #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
+        if (LITE) {
+          const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          const int c = ks * 16 + 8 * (lane >> 4);
+          ldsm_x4(qf[0][0], qf[0][1], qf[0][2], qf[0][3], sQ + r * LD + c);
+        }
+        const uint32_t* qa = qf[LITE ? 0 : ks];
   #pragma unroll
         for (int np = 0; np < 4; ++np) {  // two key n-tiles per ldmatrix.x4
           uint32_t b0, b1, b2, b3;
           const int r = np * 16 + (lane & 7) + 8 * (lane >> 4);
           const int c = ks * 16 + 8 * ((lane >> 3) & 1);
           ldsm_x4(b0, b1, b2, b3, k_s + r * LD + c);
-          mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
-          mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+          mma_bf16_16816(s[2 * np], qa, b0, b1);
+          mma_bf16_16816(s[2 * np + 1], qa, b2, b3);
         }
       }
       // ---- mask + online softmax (rows qrow0 and qrow0+8; this thread holds cols n*8 + 2*tq + {0,1})
@@ -230,12 +246,12 @@ __global__ void __launch_bounds__(BR * 2) flash_attn_kernel(const __nv_bfloat16*
   }
 }
 
-template <int HD, int HDP, bool CAUSAL, int BR>
+template <int HD, int HDP, bool CAUSAL, int BR, bool LITE>
 static int flash_launch_t(const void* Q, const void* K, const void* V, void* O, const AttnStrides& s, int B, int H,
                           int Tq, int Tk, cudaStream_t st) {
   constexpr int LD = HDP + 8;
-  constexpr int smem = (BR + 4 * 64) * LD * 2;
-  auto kern = flash_attn_kernel<HD, HDP, CAUSAL, BR>;
+  constexpr int smem = (BR + (LITE ? 2 : 4) * 64) * LD * 2;
+  auto kern = flash_attn_kernel<HD, HDP, CAUSAL, BR, LITE>;
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -268,10 +284,13 @@ int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, cons
   // B200 (profiles/r01 A/B); OVLA_ATTN_BR=128 selects the larger CTA for measurements
   static int br = -1;
   if (br < 0) { const char* ev = getenv("OVLA_ATTN_BR"); br = (ev && atoi(ev) == 128) ? 128 : 64; }
+  static int lite = -1;  // OVLA_ATTN_LITE=0 selects the double-buffered 2-CTA/SM variant
+  if (lite < 0) { const char* ev = getenv("OVLA_ATTN_LITE"); lite = (ev && ev[0] == '0') ? 0 : 1; }
   const bool big = br == 128 && Tq > 64;
 #define OVLA_ATTN(HDv, HDPv, Cv)                                                                         \
-  return big ? flash_launch_t<HDv, HDPv, Cv, 128>(Q, K, V, O, s, B, H, Tq, Tk, st)                       \
-             : flash_launch_t<HDv, HDPv, Cv, 64>(Q, K, V, O, s, B, H, Tq, Tk, st)
+  return big ? flash_launch_t<HDv, HDPv, Cv, 128, false>(Q, K, V, O, s, B, H, Tq, Tk, st)                \
+       : lite ? flash_launch_t<HDv, HDPv, Cv, 64, true>(Q, K, V, O, s, B, H, Tq, Tk, st)                 \
+              : flash_launch_t<HDv, HDPv, Cv, 64, false>(Q, K, V, O, s, B, H, Tq, Tk, st)
   if (head_dim == 64 && !causal) OVLA_ATTN(64, 64, false);
   if (head_dim == 72 && !causal) OVLA_ATTN(72, 80, false);
   if (head_dim == 128 && causal) OVLA_ATTN(128, 128, true);
