@@ -30,6 +30,11 @@ UNIT = "actions/s"
 N_LAYERS_CAPTURED = 33
 
 
+def workload_name(config: str, batch: int, prompt_len: int) -> str:
+    return (f"{config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, bs={batch}/GPU, 224px frames, "
+            f"T={256 + prompt_len + 1} (256 patches + {prompt_len + 1} prompt ids), 7 greedy action tokens")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,8 +209,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["actions_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_action"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, "
-                               f"T={256 + args.prompt_len + 1}, bs=1 sample on host CPU"},
+        "config": {"workload": workload_name(args.config, args.batch, args.prompt_len),
+                   "note": "reference arm: each step is a bs=1 sample of this workload on the host CPU"},
         "cpu_baseline": {"value": r["actions_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["actions_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -357,8 +362,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.config} predict_action + {N_LAYERS_CAPTURED}-layer mean-pooled capture, "
-                               f"bs={B}/GPU, 224px frames, T={T} (256 patches + {P0 + 1} prompt ids), 7 greedy action tokens",
+        "config": {"workload": workload_name(args.config, B, P0),
                    "global_batch": world * B, "weights": "random-init N(0,0.02) bf16, replicated per GPU",
                    "l2": "per-step working set (>40 GB of activations + 15 GB weights) exceeds the 126 MB L2; no flush needed",
                    "parallelism": f"dp{world} (observations sharded, no data-path collective)"},

@@ -148,6 +148,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   OvlaEngine* e = new OvlaEngine();
   e->d = *dims;
   if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
+  if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
   e->device = device;
   const OvlaDims& d = e->d;
   const int g = d.image_size / d.patch;
