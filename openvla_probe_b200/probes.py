@@ -545,3 +545,82 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ----------------------------------------------------------------------------------------------- packed episode store
+class PackedEpisodeStore:
+    """Streaming alternative to one `episode_N.pt` pickle per rollout: a directory with
+    `features.npy` = float32 [n_layers, N, D] (memory-mapped, appended step by step), `relations.npy` / `subgoals.npy` =
+    int8 [N, *] and `episodes.json` = [(first_row, n_rows)] per episode.  The probe trainer can map one layer slab
+    without unpickling everything; `export_reference_episodes` converts back to the reference's dict layout
+    (`run_libero_eval_object.py:357-366`) so the unmodified reference scripts can still read it."""
+
+    def __init__(self, root: str, n_layers: int = 33, dim: int = 4096, n_rel: int = 461, n_act: int = 20,
+                 capacity: int = 65536, mode: str = "w+"):
+        import json
+
+        self.root, self.n_layers, self.dim = root, n_layers, dim
+        os.makedirs(root, exist_ok=True)
+        meta_path = os.path.join(root, "episodes.json")
+        if mode == "r":
+            meta = json.load(open(meta_path))
+            self.n_layers, self.dim, n_rel, n_act, capacity = meta["n_layers"], meta["dim"], meta["n_rel"], meta["n_act"], meta["capacity"]
+            self.episodes, self.n_rows = [tuple(e) for e in meta["episodes"]], meta["n_rows"]
+        else:
+            self.episodes, self.n_rows = [], 0
+        self.n_rel, self.n_act, self.capacity = n_rel, n_act, capacity
+        mm = "r" if mode == "r" else mode
+        self.features = np.lib.format.open_memmap(os.path.join(root, "features.npy"), mode=mm, dtype=np.float32,
+                                                  shape=(self.n_layers, capacity, self.dim)) if mode != "r" else \
+            np.load(os.path.join(root, "features.npy"), mmap_mode="r")
+        self.relations = np.lib.format.open_memmap(os.path.join(root, "relations.npy"), mode=mm, dtype=np.int8,
+                                                   shape=(capacity, n_rel)) if mode != "r" else \
+            np.load(os.path.join(root, "relations.npy"), mmap_mode="r")
+        self.subgoals = np.lib.format.open_memmap(os.path.join(root, "subgoals.npy"), mode=mm, dtype=np.int8,
+                                                  shape=(capacity, n_act)) if mode != "r" else \
+            np.load(os.path.join(root, "subgoals.npy"), mmap_mode="r")
+        self._ep_start = self.n_rows
+
+    def append_batch(self, pooled: np.ndarray, rel: np.ndarray, act: np.ndarray) -> None:
+        """pooled fp32 [n_layers, B, D] straight from `predict_action_and_capture`; rel / act int8 [B, *]."""
+        B = pooled.shape[1]
+        if self.n_rows + B > self.capacity:
+            raise ValueError(f"store capacity {self.capacity} exceeded")
+        self.features[:, self.n_rows:self.n_rows + B] = pooled
+        self.relations[self.n_rows:self.n_rows + B] = rel
+        self.subgoals[self.n_rows:self.n_rows + B] = act
+        self.n_rows += B
+
+    def end_episode(self) -> None:
+        self.episodes.append((self._ep_start, self.n_rows - self._ep_start))
+        self._ep_start = self.n_rows
+
+    def flush(self) -> None:
+        import json
+
+        for a in (self.features, self.relations, self.subgoals):
+            if hasattr(a, "flush"):
+                a.flush()
+        json.dump({"n_layers": self.n_layers, "dim": self.dim, "n_rel": self.n_rel, "n_act": self.n_act,
+                   "capacity": self.capacity, "n_rows": self.n_rows, "episodes": self.episodes},
+                  open(os.path.join(self.root, "episodes.json"), "w"))
+
+    def layer(self, L: int) -> np.ndarray:
+        return self.features[L, : self.n_rows]
+
+    def as_cache(self) -> Dict[int, dict]:
+        """The `cache` dict of the trainers (train_object_probes.py:59-69) backed by the memory maps (zero copy)."""
+        out = {}
+        for i, (s, n) in enumerate(self.episodes):
+            out[i] = {"visual_semantic_encoding": {L: torch.from_numpy(np.asarray(self.features[L, s:s + n])) for L in range(self.n_layers)},
+                      "symbolic_state_object_relations": torch.from_numpy(np.asarray(self.relations[s:s + n])),
+                      "symbolic_state_action_subgoals": torch.from_numpy(np.asarray(self.subgoals[s:s + n]))}
+        return out
+
+    def export_reference_episodes(self, log_dir: str) -> None:
+        os.makedirs(log_dir, exist_ok=True)
+        for i, d in self.as_cache().items():
+            torch.save({"visual_semantic_encoding": {L: v.clone() for L, v in d["visual_semantic_encoding"].items()},
+                        "symbolic_state_object_relations": d["symbolic_state_object_relations"].clone(),
+                        "symbolic_state_action_subgoals": d["symbolic_state_action_subgoals"].clone()},
+                       os.path.join(log_dir, f"episode_{i + 1}.pt"))

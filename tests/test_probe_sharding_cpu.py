@@ -132,3 +132,31 @@ def test_split_keep_and_pos_weight_rules():
     X, Yl = layer_matrix(cache, sp.train_ids, 0)
     assert X.shape == (18 * 15, 8) and Yl.shape == (18 * 15, 16) and Yl.dtype == torch.int8
     assert layer_matrix(cache, sp.train_ids, 5)[0].numel() == 0  # layer absent -> empty (StepDS `layer in cache[...]`)
+
+
+def test_packed_episode_store_round_trip(tmp_path):
+    """Packed memory-mapped store <-> the reference's episode_*.pt dict layout (run_libero_eval_object.py:357-366)."""
+    from openvla_probe_b200.probes import PackedEpisodeStore, load_episodes
+
+    rng = np.random.default_rng(0)
+    st = PackedEpisodeStore(str(tmp_path / "store"), n_layers=3, dim=16, n_rel=5, n_act=2, capacity=64)
+    ref = []
+    for ep in range(3):
+        for _ in range(2):
+            pooled = rng.normal(size=(3, 4, 16)).astype(np.float32)
+            rel = rng.integers(-1, 2, (4, 5)).astype(np.int8)
+            act = rng.integers(-1, 2, (4, 2)).astype(np.int8)
+            st.append_batch(pooled, rel, act)
+            ref.append((ep, pooled, rel, act))
+        st.end_episode()
+    st.flush()
+    rd = PackedEpisodeStore(str(tmp_path / "store"), mode="r")
+    assert rd.n_rows == 24 and rd.episodes == [(0, 8), (8, 8), (16, 8)] and rd.layer(2).shape == (24, 16)
+    rd.export_reference_episodes(str(tmp_path / "logs"))
+    cache = load_episodes(str(tmp_path / "logs"))
+    assert len(cache) == 3
+    d = cache[1]
+    assert set(d) == {"visual_semantic_encoding", "symbolic_state_object_relations", "symbolic_state_action_subgoals"}
+    want = np.concatenate([p[1][2] for p in ref if p[0] == 1])
+    assert np.array_equal(d["visual_semantic_encoding"][2].numpy(), want)
+    assert d["symbolic_state_object_relations"].dtype == torch.int8 and d["symbolic_state_object_relations"].shape == (8, 5)
