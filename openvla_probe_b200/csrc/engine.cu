@@ -80,8 +80,11 @@ struct OvlaEngine {
   std::vector<LayerW> layers;
 
   // workspace
-  bf16 *v_im2col = nullptr, *v_patch = nullptr, *v_x = nullptr, *v_h = nullptr, *v_qkv = nullptr, *v_attn = nullptr,
-       *v_mlp = nullptr;
+  struct VitBufs { bf16 *im2col = nullptr, *patch = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *mlp = nullptr; };
+  VitBufs vb[2];            // [1] is a small second set: at B <= kTwoStreamBatch the two towers run on two streams
+  static constexpr int kTwoStreamBatch = 8;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bf16 *p_cat = nullptr, *p_1 = nullptr, *p_2 = nullptr, *p_3 = nullptr;
   bf16 *l_x = nullptr, *l_h = nullptr, *l_qkv = nullptr, *l_attn = nullptr, *l_act = nullptr;
   bf16* kv = nullptr;
@@ -90,6 +93,7 @@ struct OvlaEngine {
   int* err_flag = nullptr;
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
+  bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
   bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -148,6 +152,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   OvlaEngine* e = new OvlaEngine();
   e->d = *dims;
   if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
+  if (const char* ts = getenv("OVLA_TWO_STREAMS")) e->two_streams = ts[0] != '0';
   if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
   e->device = device;
   const OvlaDims& d = e->d;
@@ -217,13 +222,17 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
     maxMlp = std::max<long long>(maxMlp, d.towers[t].mlp);
   }
   auto W = [&](auto** p, long long n) { if (!rc) rc = e->alloc(p, n, false); };
-  W(&e->v_im2col, B * e->np * e->kpad);
-  W(&e->v_patch, B * e->np * maxD);
-  W(&e->v_x, B * maxN * maxD);
-  W(&e->v_h, B * maxN * maxD);
-  W(&e->v_qkv, B * maxN * 3 * maxD);
-  W(&e->v_attn, B * maxN * maxD);
-  W(&e->v_mlp, B * maxN * maxMlp);
+  for (int set = 0; set < (d.n_towers == 2 ? 2 : 1); ++set) {
+    const long long Bv = set == 0 ? B : std::min<long long>(B, OvlaEngine::kTwoStreamBatch);
+    OvlaEngine::VitBufs& v = e->vb[set];
+    W(&v.im2col, Bv * e->np * e->kpad);
+    W(&v.patch, Bv * e->np * maxD);
+    W(&v.x, Bv * maxN * maxD);
+    W(&v.h, Bv * maxN * maxD);
+    W(&v.qkv, Bv * maxN * 3 * maxD);
+    W(&v.attn, Bv * maxN * maxD);
+    W(&v.mlp, Bv * maxN * maxMlp);
+  }
   W(&e->p_cat, B * e->np * Dv);
   W(&e->p_1, B * e->np * std::max<long long>(4LL * Dv, Dl));
   W(&e->p_2, B * e->np * Dl);
@@ -260,6 +269,9 @@ extern "C" void ovla_destroy(OvlaEngine* e) {
   for (auto& kv : e->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   for (void* p : e->allocs) cudaFree(p);
@@ -453,34 +465,34 @@ int linear(const bf16* A, long long lda, const Slot& W, int M, int mode, void* o
   return gemm_launch(A, lda, W.ptr, K, M, N, K, mode, kKindBf16, epi, 0, 0, num_sms(), st);
 }
 
-int run_tower(OvlaEngine* e, int t, const bf16* px, int B, cudaStream_t st) {
+int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::VitBufs& v, cudaStream_t st) {
   const OvlaDims& d = e->d;
   const OvlaTower& w = d.towers[t];
   TowerW& tw = e->tower[t];
   const int np = e->np, N = np + w.n_prefix, D = w.dim, hd = D / w.heads;
   const int rows = B * N;
   // patch embed: im2col -> GEMM(+bias) -> (+pos_embed, prefix tokens)
-  OVLA_TRY(im2col_launch(px, B, 3 * d.n_towers, 3 * t, d.image_size, d.image_size, d.patch, e->kpad, e->v_im2col, st));
-  OVLA_TRY(linear(e->v_im2col, e->kpad, tw.patch_w, B * np, kModeBf16, e->v_patch, D, tw.patch_b.ptr, nullptr, nullptr,
+  OVLA_TRY(im2col_launch(px, B, 3 * d.n_towers, 3 * t, d.image_size, d.image_size, d.patch, e->kpad, v.im2col, st));
+  OVLA_TRY(linear(v.im2col, e->kpad, tw.patch_w, B * np, kModeBf16, v.patch, D, tw.patch_b.ptr, nullptr, nullptr,
                   0, 0, 0, st));
-  OVLA_TRY(assemble_tokens_launch(e->v_patch, tw.pos.ptr, tw.cls.ptr, tw.reg.ptr, B, np, w.n_prefix, D, e->v_x, st));
+  OVLA_TRY(assemble_tokens_launch(v.patch, tw.pos.ptr, tw.cls.ptr, tw.reg.ptr, B, np, w.n_prefix, D, v.x, st));
   const long long s12[12] = {3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd,
                              1LL * D * N, D, hd};
   for (int i = 0; i < e->n_run[t]; ++i) {
     BlockW& b = tw.blocks[i];
-    OVLA_TRY(layernorm_launch(e->v_x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, e->v_h, D, rows, D, st));
-    OVLA_TRY(linear(e->v_h, D, b.qkv_w, rows, kModeBf16, e->v_qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
-    OVLA_TRY(flash_attn_launch(e->v_qkv, e->v_qkv + D, e->v_qkv + 2 * D, e->v_attn, s12, B, w.heads, N, N, hd, 0, st));
+    OVLA_TRY(layernorm_launch(v.x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, v.h, D, rows, D, st));
+    OVLA_TRY(linear(v.h, D, b.qkv_w, rows, kModeBf16, v.qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(flash_attn_launch(v.qkv, v.qkv + D, v.qkv + 2 * D, v.attn, s12, B, w.heads, N, N, hd, 0, st));
     // x = x + ls1(proj(attn))   (in place: each epilogue thread reads its residual before writing)
-    OVLA_TRY(linear(e->v_attn, D, b.proj_w, rows, kModeBf16, e->v_x, D, b.proj_b.ptr, b.ls1.ptr, e->v_x, D, 0, 0, st));
-    OVLA_TRY(layernorm_launch(e->v_x, D, b.ln2_w.ptr, b.ln2_b.ptr, 1e-6f, e->v_h, D, rows, D, st));
-    OVLA_TRY(linear(e->v_h, D, b.fc1_w, rows, kModeBf16, e->v_mlp, w.mlp, b.fc1_b.ptr, nullptr, nullptr, 0, 1, 0, st));
-    OVLA_TRY(linear(e->v_mlp, w.mlp, b.fc2_w, rows, kModeBf16, e->v_x, D, b.fc2_b.ptr, b.ls2.ptr, e->v_x, D, 0, 0, st));
+    OVLA_TRY(linear(v.attn, D, b.proj_w, rows, kModeBf16, v.x, D, b.proj_b.ptr, b.ls1.ptr, v.x, D, 0, 0, st));
+    OVLA_TRY(layernorm_launch(v.x, D, b.ln2_w.ptr, b.ln2_b.ptr, 1e-6f, v.h, D, rows, D, st));
+    OVLA_TRY(linear(v.h, D, b.fc1_w, rows, kModeBf16, v.mlp, w.mlp, b.fc1_b.ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(v.mlp, w.mlp, b.fc2_w, rows, kModeBf16, v.x, D, b.fc2_b.ptr, b.ls2.ptr, v.x, D, 0, 0, st));
   }
   // strip prefix tokens, concat on the feature dim (modeling_prismatic.py:123)
   int col0 = 0;
   for (int u = 0; u < t; ++u) col0 += d.towers[u].dim;
-  OVLA_TRY(copy_rows_launch(e->v_x, 1LL * N * D, D, w.n_prefix, e->p_cat, 1LL * np * e->vision_dim, e->vision_dim, col0,
+  OVLA_TRY(copy_rows_launch(v.x, 1LL * N * D, D, w.n_prefix, e->p_cat, 1LL * np * e->vision_dim, e->vision_dim, col0,
                             B, np, D, st));
   return 0;
 }
@@ -584,7 +596,24 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
   // The KV cache is laid out for the live batch: [B, H, max_seq, hd] per layer half (capacity max_batch).
 
   // ---- vision towers + projector
-  for (int t = 0; t < d.n_towers; ++t) OVLA_TRY(run_tower(e, t, static_cast<const bf16*>(a->pixel_values_dev), B, st));
+  const bf16* px = static_cast<const bf16*>(a->pixel_values_dev);
+  if (d.n_towers == 2 && B <= OvlaEngine::kTwoStreamBatch && e->two_streams) {
+    // small batches are latency-bound: the two independent towers run concurrently on two streams (fork / join with
+    // events, which also captures into the CUDA graph as two parallel branches)
+    if (!e->side_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    OVLA_TRY(run_tower(e, 0, px, B, e->vb[0], st));
+    OVLA_TRY(run_tower(e, 1, px, B, e->vb[1], e->side_stream));
+    CUDA_TRY(cudaEventRecord(e->ev_join, e->side_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
+  } else {
+    for (int t = 0; t < d.n_towers; ++t) OVLA_TRY(run_tower(e, t, px, B, e->vb[0], st));
+  }
   const int Mp = B * np, Dv = e->vision_dim;
   if (a->patches_out_dev)
     CUDA_TRY(cudaMemcpyAsync(a->patches_out_dev, e->p_cat, sizeof(bf16) * Mp * Dv, cudaMemcpyDeviceToDevice, st));
