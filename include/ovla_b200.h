@@ -72,9 +72,6 @@ int ovla_rmsnorm(const void* x_dev, long long ldx, const void* w_dev, float eps,
 int ovla_flash_attention(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev,
                          const long long* strides12, int B, int H, int Tq, int Tk, int head_dim, int causal,
                          void* stream);
-/* one-query attention over a KV cache [B, H, Tmax, 128] (cached generation, modeling_prismatic.py:325-341) */
-int ovla_decode_attention(const void* q_dev, long long q_ld, const void* k_cache_dev, const void* v_cache_dev, int B,
-                          int H, int head_dim, int Tmax, int ctx, void* out_dev, long long o_ld, void* stream);
 /* in-place RoPE on q of a fused [B*T, 3*H*hd] qkv buffer + rotated-k / v write into the KV cache at pos0+t */
 int ovla_rope_kv(void* qkv_dev, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
                  void* k_cache_dev, void* v_cache_dev, int Tmax, void* stream);

@@ -104,10 +104,6 @@ int ovla_flash_attention(const void* q, const void* k, const void* v, void* o, c
   if (!strides12) return set_error("ovla_flash_attention: null strides");
   return flash_attn_launch(q, k, v, o, strides12, B, H, Tq, Tk, head_dim, causal, static_cast<cudaStream_t>(stream));
 }
-int ovla_decode_attention(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
-                          int Tmax, int ctx, void* out, long long o_ld, void* stream) {
-  return decode_attn_launch(q, q_ld, kc, vc, B, H, head_dim, Tmax, ctx, out, o_ld, static_cast<cudaStream_t>(stream));
-}
 int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
                                void* kc, void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
                                void* stream) {

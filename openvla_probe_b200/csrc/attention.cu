@@ -6,8 +6,7 @@
 //    tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate).  Attention is < 1 % of the path's flops
 //    (21.8 of 4157 GFLOP per action), so this kernel is sized for correctness and low traffic; the
 //    tcgen05 budget goes to the GEMMs that carry 99 % of the work.
-//  * decode_attn_kernel: single-query attention over the KV cache for the 6 cached decode steps -- pure
-//    HBM streaming of K and V ([ctx, 128] bf16 each per (batch, head)), 16-byte coalesced loads.
+//  (the cached-decode attention lives in decode.cu, fused with RoPE and the KV append)
 // Softmax is computed in fp32 and probabilities are rounded to bf16 before the PV product, as flash-attn does.
 #include <stdlib.h>
 
@@ -298,116 +297,6 @@ int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, cons
   if (head_dim == 64 && causal) OVLA_ATTN(64, 64, true);
 #undef OVLA_ATTN
   return set_error("attention: unsupported head_dim=%d causal=%d", head_dim, causal);
-}
-
-// ------------------------------------------------------------------------------------------- decode attention
-// q [B, H, HD] (row stride q_ld per batch), cache K/V [B, H, Tmax, HD]; ctx keys valid; out [B, H*HD].
-// CTA per (h, b), 128 threads.  Phase 1: half-warp per key, 16-byte loads, shuffle-reduced dot products.
-// Phase 2: softmax over smem scores.  Phase 3: thread d accumulates sum_j p_j V[j][d] (coalesced rows).
-template <int HD>
-__global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld,
-                                                          const __nv_bfloat16* __restrict__ kc,
-                                                          const __nv_bfloat16* __restrict__ vc, int Tmax, int ctx,
-                                                          __nv_bfloat16* __restrict__ out, long long o_ld,
-                                                          float scale) {
-  static_assert(HD == 128, "decode attention is specialised for head_dim 128");
-  extern __shared__ float sc[];  // [ctx]
-  __shared__ float red[4];
-  const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hl = lane & 15, half = lane >> 4;
-  const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * H + h) * Tmax * HD;
-  const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * H + h) * Tmax * HD;
-  float qv[8];
-  {
-    const uint4 u = *reinterpret_cast<const uint4*>(q + b * q_ld + h * HD + hl * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(w[i]);
-      qv[2 * i] = f.x;
-      qv[2 * i + 1] = f.y;
-    }
-  }
-  for (int j0 = warp * 2; j0 < ctx; j0 += 8) {
-    const int j = j0 + half;
-    float d = 0.f;
-    if (j < ctx) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * HD + hl * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16(w[i]);
-        d += f.x * qv[2 * i] + f.y * qv[2 * i + 1];
-      }
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (hl == 0 && j < ctx) sc[j] = d * scale;
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = tid; j < ctx; j += 128) mx = fmaxf(mx, sc[j]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  float sum = 0.f;
-  for (int j = tid; j < ctx; j += 128) {
-    const float p = __expf(sc[j] - mx);
-    sc[j] = p;
-    sum += p;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) red[warp] = sum;
-  __syncthreads();
-  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
-  // phase 3: 16 lanes x 8 dims cover a 256-byte V row; 8 row-groups (128 threads / 16) stride over keys
-  const int grp = tid >> 4;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int j = grp; j < ctx; j += 8) {
-    const float p = bf16_round(sc[j] * inv);
-    const uint4 u = *reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * HD + hl * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(w[i]);
-      acc[2 * i] += p * f.x;
-      acc[2 * i + 1] += p * f.y;
-    }
-  }
-  __syncthreads();  // scores no longer needed: reuse smem for the cross-group reduction
-  float* ra = sc;   // needs 8 * 128 floats (host guarantees the allocation)
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ra[grp * HD + hl * 8 + i] = acc[i];
-  __syncthreads();
-  float o = 0.f;
-#pragma unroll
-  for (int gI = 0; gI < 8; ++gI) o += ra[gI * HD + tid];
-  out[b * o_ld + h * HD + tid] = __float2bfloat16_rn(o);
-}
-
-int decode_attn_launch(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
-                       int Tmax, int ctx, void* out, long long o_ld, cudaStream_t st) {
-  if (B <= 0) return 0;
-  if (head_dim != 128) return set_error("decode attention: head_dim %d unsupported (128 only)", head_dim);
-  if (ctx <= 0 || ctx > Tmax) return set_error("decode attention: ctx=%d out of range (Tmax=%d)", ctx, Tmax);
-  const int smem = (ctx > 8 * 128 ? ctx : 8 * 128) * sizeof(float);
-  if (smem > 48 * 1024) return set_error("decode attention: ctx=%d too long", ctx);
-  dim3 grid(H, B);
-  ProfScope prof(kCatDecodeAttn, 4.0 * B * H * ctx * head_dim, 4.0 * B * H * ctx * head_dim + 4.0 * B * H * head_dim, st);
-  decode_attn_kernel<128><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(q), q_ld,
-                                                   static_cast<const __nv_bfloat16*>(kc),
-                                                   static_cast<const __nv_bfloat16*>(vc), Tmax, ctx,
-                                                   static_cast<__nv_bfloat16*>(out), o_ld,
-                                                   1.0f / sqrtf(static_cast<float>(head_dim)));
-  CUDA_TRY(cudaGetLastError());
-  count_launch();
-  return 0;
 }
 
 }  // namespace ovla

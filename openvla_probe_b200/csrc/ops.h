@@ -30,8 +30,6 @@ int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void*
 // attention.cu
 int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
                       int Tq, int Tk, int head_dim, int causal, cudaStream_t st);
-int decode_attn_launch(const void* q, long long q_ld, const void* kc, const void* vc, int B, int H, int head_dim,
-                       int Tmax, int ctx, void* out, long long o_ld, cudaStream_t st);
 
 // elementwise.cu
 int im2col_launch(const void* px, int B, int c_total, int c0, int H, int W, int patch, int Kpad, void* out,

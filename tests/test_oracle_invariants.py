@@ -33,7 +33,7 @@ def test_llama_restatement_matches_installed_transformers():
             assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
         assert torch.allclose(O.lm_head(W, last), ref.logits, rtol=1e-4, atol=1e-4)
         # hidden_states[L] is post-final-norm
-        assert torch.allclose(hs[-1], m.model.norm(ref.hidden_states[-1]) if False else ref.hidden_states[-1], atol=1e-5)
+        assert torch.allclose(hs[-1], ref.hidden_states[-1], atol=1e-5)
         # cached single-token step: position = cache length (modeling_prismatic.py:330-341)
         tok = torch.tensor([[5], [7]])
         ref2 = m(input_ids=tok, past_key_values=ref.past_key_values, use_cache=True, return_dict=True)
@@ -120,23 +120,27 @@ def test_token_29871_append_rule(tiny):
     assert s1.shape[1] == 7 + 1 + 2
 
 
-def test_eos_policy_matches_hf_generate(tiny):
-    """If id 2 is generated early, generation stops and generated_ids[0,-7:] reaches back into the prompt."""
+def test_eos_policy_matches_hf_generate(tiny, monkeypatch):
+    """If id 2 (EOS) is generated early, HF greedy search stops and `generated_ids[0, -7:]` (modeling_prismatic.py:521)
+    reaches back into the prompt.  EOS is forced by biasing its logit."""
     d, W = tiny
-    W = dict(W)
-    lm = W["language_model.lm_head.weight"].clone()
-    lm[2] = 0.0
-    lm[2, :] = W["language_model.model.norm.weight"].sign() * 5.0     # make EOS win every argmax
-    W["language_model.lm_head.weight"] = lm
+    real_lm_head = O.lm_head
+
+    def biased(Wd, x):
+        lg = real_lm_head(Wd, x)
+        lg[..., 2] += 1e4
+        return lg
+
+    monkeypatch.setattr(O, "lm_head", biased)
     ids, px = O.make_inputs(d, 1, prompt_len=9)
     st = O.default_stats()
     with torch.no_grad():
         seq, logits, _ = O.greedy_generate(W, d, torch.cat([ids, torch.tensor([[29871]])], 1), px.float(), 7,
                                            dtype=torch.float32)
         acts, toks = O.predict_action(W, d, ids, px.float(), st, dtype=torch.float32, return_tokens=True)
-    if int(seq[0, 10]) == 2:
-        assert seq.shape[1] == 11                                      # stopped after one token
-        assert toks[0].tolist() == torch.cat([ids[0], torch.tensor([29871, 2])])[-7:].tolist()
+    assert seq.shape[1] == 11 and int(seq[0, 10]) == 2                # stopped after one generated token
+    assert toks[0].tolist() == torch.cat([ids[0], torch.tensor([29871, 2])])[-7:].tolist()
+    assert np.array_equal(acts[0], O.unnormalize(O.detokenize(toks[0], d), st))
 
 
 def test_pool_modes_and_layer_indices(tiny):
