@@ -2,7 +2,10 @@
 #include <stdlib.h>
 
 #include "gemm.cuh"
+#include <algorithm>
+
 #include "host_util.h"
+#include "ops.h"
 
 namespace ovla {
 
@@ -51,7 +54,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSh
     attr_set = true;
   }
   const int tile_m = kBM * CG;
-  const int tiles = ((s.M + tile_m - 1) / tile_m) * ((s.N + BN - 1) / BN);
+  const int tiles = ((s.M + tile_m - 1) / tile_m) * ((s.N + BN - 1) / BN) * s.split_k;
   int workers = num_sms / CG;
   if (workers > tiles) workers = tiles;
   cudaLaunchConfig_t cfg = {};
@@ -97,6 +100,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
       return set_error("gemm: fused QKV+RoPE needs cos/sin tables, KV caches and M = B * T");
     if (epi.pos0 + epi.T > epi.Tmax) return set_error("gemm: position %d exceeds KV capacity %d", epi.pos0 + epi.T, epi.Tmax);
   }
+  const bool auto_tile = bn <= 0;
   if (bn <= 0) {
     // Tile heuristic.  Large problems: CTA-pair 256x256 tiles (tensor-bound).  Small M (bs=1 prefill, M = 261..288,
     // and the batched decode steps, M = B): the GEMM is a weight stream whose speed is set by shared-memory fill
@@ -114,15 +118,58 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   }
   if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");
   if (mode == kModeQkvRope && bn < 128) { bn = 128; cg = 1; }  // a tile must hold whole 128-wide heads
+  // rasterisation group (tools/gemm_group_sweep.py, profiles/r01_gemm_group_sweep.jsonl): 16 row-tiles keep the
+  // activation slab of a group L2-resident while the weights stream; narrow, short-K problems prefer 8
+  static int g_group = -1, g_split = -2;
+  if (g_group < 0) { const char* ev = getenv("OVLA_GEMM_GROUP"); g_group = (ev && atoi(ev) > 0) ? atoi(ev) : 0; }
+  if (g_split == -2) { const char* ev = getenv("OVLA_SPLITK"); g_split = ev ? atoi(ev) : -1; }  // -1 auto, 0/1 off, n forced
+  const int group = g_group > 0 ? g_group : ((N <= 4096 && K <= 4096) ? 8 : 16);
+
+  // split-K for the small-M weight-streaming shapes (see splitk.cu)
+  const int num_k = (K + (128 / eb) - 1) / (128 / eb);
+  int split = 1;
+  if (auto_tile && g_split != 0 && g_split != 1 && M <= 512 && kind == kKindBf16 &&
+      (mode == kModeBf16 || mode == kModeSwiGLU || mode == kModeF32) && (mode == kModeSwiGLU ? (N / 2) % 8 == 0 : N % 8 == 0)) {
+    if (N < 8192) { bn = 128; cg = 1; }
+    const long long tiles_mn = ((M + 128LL * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+    // pick the slice count that minimises (waves of CTAs) x (K blocks per slice) + the reduce kernel (fixed cost +
+    // its fp32 workspace traffic at ~2 MB per unit), in units of one K block (~0.35 us); split only long-K problems
+    // and only for a >= 15 % modelled gain (calibrated on tools/gemm_smallm_bench.py)
+    int want = 1;
+    if (g_split > 1) {
+      want = g_split;
+    } else if (num_k >= 32) {
+      const long long slots = num_sms / cg;
+      long long best = ((tiles_mn + slots - 1) / slots) * num_k;
+      const long long base = best;
+      for (int S = 2; S <= 8 && num_k / S >= 8; ++S) {
+        const long long cost = ((tiles_mn * S + slots - 1) / slots) * ((num_k + S - 1) / S) + 8 +
+                               (8LL * S * M * N) / (2 << 20);
+        if (cost < best) { best = cost; want = S; }
+      }
+      if (best * 100 > base * 85) want = 1;
+    }
+    want = std::min(want, 8);
+    while (want >= 2 && 1LL * want * M * N > splitk_workspace_floats()) --want;
+    if (want >= 2 && splitk_workspace()) {
+      const int kps = (num_k + want - 1) / want;
+      split = (num_k + kps - 1) / kps;
+    }
+  }
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, A, eb, M, K, lda, kBM)) return -1;
   if (make_tmap_2d(&tb, W, eb, N, K, ldw, bn / cg)) return -1;
-  // rasterisation group (tools/gemm_group_sweep.py, profiles/r01_gemm_group_sweep.jsonl): 16 row-tiles keep the
-  // activation slab of a group L2-resident while the weights stream; narrow, short-K problems prefer 8
-  static int g_group = -1;
-  if (g_group < 0) { const char* ev = getenv("OVLA_GEMM_GROUP"); g_group = (ev && atoi(ev) > 0) ? atoi(ev) : 0; }
-  const int group = g_group > 0 ? g_group : ((N <= 4096 && K <= 4096) ? 8 : 16);
-  GemmShape s{M, N, K, group};
+  if (split >= 2) {
+    const int kps = (num_k + split - 1) / split;
+    GemmShape s{M, N, K, group, split, kps};
+    GemmEpi pe = {};
+    pe.out = splitk_workspace();
+    pe.ldo = N;
+    pe.ldr = 1LL * M * N;  // slice stride
+    OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, s, pe, num_sms, stream)));
+    return splitk_epilogue_launch(mode, splitk_workspace(), 1LL * M * N, N, split, M, N, epi, stream);
+  }
+  GemmShape s{M, N, K, group, 1, num_k};
   if (kind == kKindBf16) {
     if (mode == kModeBf16) return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
     if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);

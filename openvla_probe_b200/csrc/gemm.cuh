@@ -25,6 +25,7 @@ enum GemmMode : int {
   kModeSwiGLU = 1,  // W rows interleaved [32 gate | 32 up]; out[M, N/2] = silu(g) * u
   kModeF32 = 2,     // fp32 out; optional fp32-or-bf16 bias; optional rounding of the value to bf16
   kModeQkvRope = 3, // fused Llama QKV projection: RoPE on q/k, q written back, rotated k and v written to the KV cache
+  kModePartial = 4, // split-K: raw fp32 partial sums of this tile's K slice -> out + slice * ldr (reduced by splitk_epilogue)
 };
 enum GemmKind : int { kKindBf16 = 0, kKindTf32 = 1 };
 
@@ -49,6 +50,8 @@ struct GemmEpi {
 struct GemmShape {
   int M, N, K;  // N = rows of W (pre-epilogue output columns); K in elements
   int group_m;  // rasterisation group size (row-tiles)
+  int split_k;  // K slices (each tile of a slice accumulates kb_per_split K blocks); 1 = no split
+  int kb_per_split;
 };
 
 static constexpr int kGemmThreads = 384;
@@ -102,7 +105,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int num_m = (shape.M + kTileM - 1) / kTileM;
   const int num_n = (shape.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int tiles_mn = num_m * num_n;
+  const int num_tiles = tiles_mn * shape.split_k;
   const int num_k = (shape.K + kKElems - 1) / kKElems;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
@@ -138,10 +142,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int t = worker; t < num_tiles; t += num_workers) {
         int mb, nb;
-        gemm_tile_coords(t, num_m, num_n, shape.group_m, mb, nb);
+        const int slice = t / tiles_mn;
+        gemm_tile_coords(t - slice * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
         const int row_a = mb * kTileM + static_cast<int>(cta_rank) * kBM;
         const int row_b = nb * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
@@ -170,7 +176,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int slice = t / tiles_mn;
+        const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -179,9 +187,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 MMAs of 32 bytes of K each per 128-byte block
             if constexpr (KIND == kKindBf16)
-              umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
             else
-              umma_tf32<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_tf32<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -198,7 +206,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     for (int t = worker; t < num_tiles; t += num_workers) {
       int mb, nb;
-      gemm_tile_coords(t, num_m, num_n, shape.group_m, mb, nb);
+      const int slice = t / tiles_mn;
+      gemm_tile_coords(t - slice * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
@@ -356,6 +365,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               *reinterpret_cast<uint4*>(d1 + g * 8) = w1;
               *reinterpret_cast<uint4*>(d1 + 64 + g * 8) = w2;
             }
+          }
+        }
+      } else if constexpr (MODE == kModePartial) {
+        float* out = reinterpret_cast<float*>(epi.out) + static_cast<long long>(slice) * epi.ldr +
+                     static_cast<long long>(row) * epi.ldo;
+#pragma unroll 1
+        for (int c = part; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col = col0 + c * 32;
+          if (col >= shape.N || !row_ok) continue;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int cg = col + g * 4;
+            if (cg >= shape.N) break;
+            *reinterpret_cast<float4*>(out + cg) =
+                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                            __uint_as_float(v[g * 4 + 3]));
           }
         }
       } else {  // kModeF32

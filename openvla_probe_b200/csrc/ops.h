@@ -13,6 +13,11 @@ int num_sms();
 // gemm.cu -- tcgen05 GEMM
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
                 const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream);
+// splitk.cu -- split-K workspace + reduce/epilogue
+float* splitk_workspace();
+long long splitk_workspace_floats();
+int splitk_epilogue_launch(int mode, const float* ws, long long slice_stride, long long ldw, int S, int M, int N,
+                           const GemmEpi& epi, cudaStream_t st);
 // gemv.cu -- M <= 8 weight streaming
 int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, int mode,
                 const GemmEpi& epi, cudaStream_t st);

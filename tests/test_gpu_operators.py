@@ -333,3 +333,41 @@ def test_preprocess_frames_bit_exact_and_native_twin():
     ids = torch.tensor([hash_tokenizer(pb.get_prompt())])
     a_hf = model.predict_action(ids, unnorm_key="synthetic", pixel_values=px_host[:1])
     assert a_native.shape == (7,) and np.array_equal(a_native, a_hf)
+
+
+@pytest.mark.parametrize("M,N,K,mode,expect_split", [(288, 4096, 11008, 0, True), (256, 4096, 11008, 0, True),
+                                                     (261, 1024, 4096, 0, True), (128, 2048, 4096, 1, True),
+                                                     (64, 2048, 8192, 2, True), (300, 12288, 4096, 0, False)])
+def test_splitk_small_m_gemm(L, M, N, K, mode, expect_split):
+    """Small-M shapes go through split-K (partial tiles + ordered reduce/epilogue kernel) under the library heuristic;
+    same tolerance as the fused epilogue."""
+    _lib, lib = L
+    g = torch.Generator().manual_seed(N + K)
+    A = bf(torch.randn(M, K, generator=g) * 0.5).cuda()
+    W = bf(torch.randn(N, K, generator=g) * 0.03).cuda()
+    epi = _lib.GemmEpilogue()
+    ref = A.float() @ W.float().t()
+    if mode == 0:
+        bias, resid = bf(torch.randn(N, generator=g) * 0.1).cuda(), bf(torch.randn(M, N, generator=g)).cuda()
+        epi.bias_bf16, epi.resid_bf16, epi.ld_resid = bias.data_ptr(), resid.data_ptr(), N
+        ref = (ref + bias.float()).bfloat16().float() + resid.float()
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        n_out = N
+    elif mode == 1:
+        r3 = ref.view(M, N // 64, 2, 32)
+        gte, up = r3[:, :, 0].reshape(M, -1).bfloat16().float(), r3[:, :, 1].reshape(M, -1).bfloat16().float()
+        ref = F.silu(gte).bfloat16().float() * up
+        out = torch.empty(M, N // 2, dtype=torch.bfloat16, device="cuda")
+        n_out = N // 2
+    else:
+        epi.round_bf16 = 1
+        ref = ref.bfloat16().float()
+        out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+        n_out = N
+    before = lib.ovla_launch_count()
+    _lib.check(lib.ovla_gemm(P(A), C.c_longlong(K), P(W), C.c_longlong(K), M, N, K, mode, 0, P(out), C.c_longlong(n_out),
+                             C.byref(epi), 0, 0, None))
+    # 2 launches = partial GEMM + ordered reduce/epilogue kernel (the split-K path); 1 = plain fused GEMM
+    assert lib.ovla_launch_count() - before == (2 if expect_split else 1)
+    ok, e = close_bf16(out, ref, ulps=3.0)
+    assert ok, e

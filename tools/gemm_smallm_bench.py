@@ -10,7 +10,7 @@ SHAPES = [("qkv", 288, 12288, 4096, 0), ("o", 288, 4096, 4096, 0), ("gate_up", 2
           ("vit_qkv", 261, 3072, 1024, 0), ("vit_fc1", 261, 4096, 1024, 0), ("vit_fc2", 261, 1024, 4096, 0), ("sig_fc1", 256, 4304, 1152, 0)]
 if MM:
     SHAPES = [(n, MM, N, K, mode) for n, _, N, K, mode in SHAPES[:4]] + [("lm_head", MM, 32064, 4096, 2)]
-CFGS = [(64, 1), (128, 1), (128, 2), (256, 1), (256, 2)]
+CFGS = [(0, 0), (64, 1), (128, 1), (256, 1), (256, 2)]   # (0, 0) = library heuristic (incl. split-K unless OVLA_SPLITK=0)
 os.makedirs("gpurun_out", exist_ok=True)
 f = open(f"gpurun_out/gemm_smallm_M{MM}.jsonl", "w")
 for name, M, N, K, mode in SHAPES:
