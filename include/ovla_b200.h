@@ -72,6 +72,16 @@ int ovla_rmsnorm(const void* x_dev, long long ldx, const void* w_dev, float eps,
 int ovla_flash_attention(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev,
                          const long long* strides12, int B, int H, int Tq, int Tk, int head_dim, int causal,
                          void* stream);
+/* Causal self-attention of a prefill on the tcgen05 tensor cores (head_dim 128 only): rotated queries in the fused
+ * qkv buffer [B*T, ld_q] (head h at columns h*128), keys / values in the cache [B, H, Tmax, 128] whose rows >= T must
+ * hold finite values; out [B*T, ldo].  Same math as ovla_flash_attention(causal=1) (LlamaAttention via SDPA,
+ * transformers modeling_llama.py; called from prismatic/extern/hf/modeling_prismatic.py:330-341). */
+int ovla_prefill_attention_tc(const void* q_dev, long long ld_q, const void* k_cache_dev, const void* v_cache_dev,
+                              void* out_dev, long long ldo, int B, int H, int T, int Tmax, void* stream);
+/* The same tensor-core kernel for q | k | v packed in one [B*T, 3*H*hd] buffer (timm Attention.qkv output,
+ * modeling_prismatic.py:85-87 towers): head_dim 64 or 128, causal 0/1. */
+int ovla_attention_tc_qkv(const void* qkv_dev, long long ld, void* out_dev, long long ldo, int B, int H, int T,
+                          int head_dim, int causal, void* stream);
 /* in-place RoPE on q of a fused [B*T, 3*H*hd] qkv buffer + rotated-k / v write into the KV cache at pos0+t */
 int ovla_rope_kv(void* qkv_dev, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
                  void* k_cache_dev, void* v_cache_dev, int Tmax, void* stream);

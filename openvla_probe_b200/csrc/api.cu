@@ -104,6 +104,14 @@ int ovla_flash_attention(const void* q, const void* k, const void* v, void* o, c
   if (!strides12) return set_error("ovla_flash_attention: null strides");
   return flash_attn_launch(q, k, v, o, strides12, B, H, Tq, Tk, head_dim, causal, static_cast<cudaStream_t>(stream));
 }
+int ovla_prefill_attention_tc(const void* q, long long ld_q, const void* kc, const void* vc, void* out, long long ldo,
+                              int B, int H, int T, int Tmax, void* stream) {
+  return attn_tc_prefill_launch(q, ld_q, kc, vc, out, ldo, B, H, T, Tmax, static_cast<cudaStream_t>(stream));
+}
+int ovla_attention_tc_qkv(const void* qkv, long long ld, void* out, long long ldo, int B, int H, int T, int head_dim,
+                          int causal, void* stream) {
+  return attn_tc_qkv_launch(qkv, ld, out, ldo, B, H, T, head_dim, causal, static_cast<cudaStream_t>(stream));
+}
 int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
                                void* kc, void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
                                void* stream) {

@@ -1,0 +1,378 @@
+// tcgen05 / TMEM flash attention: the causal Llama prefill (head_dim 128, K/V in the cache layout) and the
+// non-causal head_dim-64 ViT tower (q, k, v packed in one [B*T, 3D] buffer).
+//
+// One CTA = 128 query rows of one (batch, head); keys are consumed in chunks of 64 with an online softmax.
+//   warp 4      TMA producer: Q tile once, then K/V chunks into a 2-stage ring (128B-swizzled)
+//   warp 5      MMA issuer:   S_c[128 x 64]  = Q . K_c^T   (SS, both K-major)            -> TMEM cols [64*(c&1), +64)
+//                             O  [128 x HD] += P_c . V_c   (V as an MN-major B operand, i.e. exactly as it lies in
+//                                                           memory: [key][hd])            -> TMEM cols [128, 128+HD)
+//               S_{c+1} is issued before the PV product of chunk c, so the tensor core computes the next scores
+//               while the softmax warps work on the current ones.
+//   warps 0-3   softmax: thread r owns query row r (= TMEM lane r): tcgen05.ld the 64 scores, mask, p = exp2(..),
+//               P_c -> bf16 into shared memory in the K-major 128B-swizzle layout the tensor core reads.
+// O accumulates in TMEM across chunks.  The running max is only refreshed (and O, l rescaled with a TMEM
+// load-multiply-store) when a row's max grows by more than 2^8 relative to the reference it is using, so the rescale
+// is rare; probabilities are bounded by 256 in that frame, which bf16 and the fp32 accumulators hold exactly as well
+// as values <= 1.  Probabilities are rounded to bf16 before the PV product, as flash-attn does.
+// Tiles are aligned to the END of the sequence (the ragged tile is the first one, which under the causal mask has the
+// fewest keys), and the last chunk of a tile is shortened to a multiple of 16 keys.
+// head_dim 128: P_c is written over K_c (dead once S_c is complete) -> 96 KB of shared memory, 256 TMEM columns:
+// two CTAs per SM.  head_dim 64: 80 KB with separate P buffers.
+#include <stdlib.h>
+
+#include "host_util.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace ovla {
+
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows);  // gemm.cu
+
+static constexpr int kTcThreads = 192;       // warps 0..3 softmax / epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
+static constexpr int kTcBC = 64;             // keys per chunk
+static constexpr int kSlabQ = 128 * 128;     // bytes of a [128 rows x 128 B] swizzled slab (Q, P)
+static constexpr int kSlabKV = kTcBC * 128;  // bytes of a [64 rows x 128 B] slab (K, V chunk)
+static constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major B operand (rows = K index, each 128-byte row = 64 contiguous N elements), SWIZZLE_128B: the N extent of an
+// MMA spans 64-element slabs LBO bytes apart; groups of 8 K rows are SBO = 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  long long ldo;
+  int T, H;
+  int q_col_per_h;                        // query columns of head h start at h * q_col_per_h
+  int kv_rows_per_b, kv_rows_per_h;       // first key row of (b, h) in the K / V tensor maps
+  int k_col0, v_col0, kv_col_per_h;       // first column of head h: col0 + h * kv_col_per_h
+  float scale_log2;
+};
+
+template <int HD>
+struct AttnTcCfg {
+  static constexpr int kNS = HD / 64;                       // 64-column slabs per operand
+  static constexpr bool kAliasP = (HD == 128);              // P_c overwrites K_c
+  static constexpr int kQBytes = kNS * kSlabQ;
+  static constexpr int kStageBytes = 2 * kNS * kSlabKV;     // K chunk + V chunk
+  static constexpr int kPOff = kQBytes + 2 * kStageBytes;
+  static constexpr int kBarOff = kPOff + (kAliasP ? 0 : 2 * kSlabQ);
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;   // + barriers + alignment slack
+  static constexpr int kTmemCols = 256;                     // S ping-pong [0,128) | O [128, 128+HD)
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+  using Cfg = AttnTcCfg<HD>;
+  constexpr int NS = Cfg::kNS;
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  auto sK = [&](int s) { return smem + Cfg::kQBytes + s * Cfg::kStageBytes; };
+  auto sV = [&](int s) { return smem + Cfg::kQBytes + s * Cfg::kStageBytes + NS * kSlabKV; };
+  auto sP = [&](int s) { return Cfg::kAliasP ? sK(s) : smem + Cfg::kPOff + s * kSlabQ; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_full = bars + 1;    // [2] K/V chunk landed
+  uint64_t* bar_empty = bars + 3;   // [2] PV product of the chunk retired: stage (and P) free, O holds chunks [0, c]
+  uint64_t* bar_s = bars + 5;       // [2] scores ready in TMEM
+  uint64_t* bar_p = bars + 7;       // [2] probabilities in shared memory (128 arrivals)
+  uint64_t* bar_done = bars + 9;    // last PV product retired (single phase: waiters that skipped phases cannot alias)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = gridDim.x;
+  const int tile = n_tiles - 1 - static_cast<int>(blockIdx.x);  // longest (last) tile first
+  const int q0 = p.T - 128 * (n_tiles - tile);                  // may be negative for tile 0: those rows are dropped
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k_limit = CAUSAL ? q0 + 128 : p.T;                  // keys [0, k_limit); q0 + 128 <= T by construction
+  const int n_chunks = (k_limit + kTcBC - 1) / kTcBC;
+  const int n_last = ((k_limit - (n_chunks - 1) * kTcBC) + 15) & ~15;  // keys issued for the last chunk (16..64)
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + s, 1);
+      mbar_init(bar_empty + s, 1);
+      mbar_init(bar_s + s, 1);
+      mbar_init(bar_p + s, 128);
+    }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc<1>(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int q_col = h * p.q_col_per_h, q_row = b * p.T + q0;
+      mbar_expect_tx(bar_q, Cfg::kQBytes);
+#pragma unroll
+      for (int sl = 0; sl < NS; ++sl) tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, q_col + sl * 64, q_row);
+      const int kv_row = b * p.kv_rows_per_b + h * p.kv_rows_per_h;
+      const int k_col = p.k_col0 + h * p.kv_col_per_h, v_col = p.v_col0 + h * p.kv_col_per_h;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c & 1;
+        if (c >= 2) mbar_wait(bar_empty + s, ((c >> 1) - 1) & 1);
+        mbar_expect_tx(bar_full + s, Cfg::kStageBytes);
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl)
+          tma_load_2d(&tmap_k, bar_full + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl)
+          tma_load_2d(&tmap_v, bar_full + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1, 128, 0);                    // N filled in per chunk
+      constexpr uint32_t idesc_o = umma_idesc(1, 128, HD) | (1u << 16);      // B (= V) is MN-major
+      mbar_wait(bar_q, 0);
+      for (int c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+          const int s = c & 1;
+          const int nc = (c == n_chunks - 1) ? n_last : kTcBC;
+          mbar_wait(bar_full + s, (c >> 1) & 1);
+          tc_fence_after();
+          const uint32_t idesc = idesc_s | (static_cast<uint32_t>(nc >> 3) << 17);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const uint64_t a = umma_desc_sw128(smem_u32(sQ + (ks >> 2) * kSlabQ)) + 2 * (ks & 3);
+            const uint64_t bd = umma_desc_sw128(smem_u32(sK(s) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
+            umma_bf16<1>(tmem + s * kTcBC, a, bd, idesc, ks != 0);
+          }
+          umma_commit(bar_s + s);
+        }
+        if (c > 0) {
+          const int cp = c - 1, s = cp & 1;
+          const int nc = (cp == n_chunks - 1) ? n_last : kTcBC;
+          mbar_wait(bar_p + s, (cp >> 1) & 1);
+          tc_fence_after();
+          for (int j = 0; j < nc / 16; ++j) {
+            const uint64_t a = umma_desc_sw128(smem_u32(sP(s))) + 2 * j;
+            const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(s) + j * 16 * 128), kSlabKV);
+            umma_bf16<1>(tmem + 128, a, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + s);
+          if (cp == n_chunks - 1) umma_commit(bar_done);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax: thread = row
+    const int r = tid;
+    const int t_row = q0 + r;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    float m_ref = 0.f, l_run = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c & 1;
+      const int key0 = c * kTcBC;
+      int n_valid = k_limit - key0;
+      if (CAUSAL) n_valid = max(0, min(n_valid, t_row - key0 + 1));
+      const bool all_valid = __all_sync(0xffffffffu, n_valid >= kTcBC);
+      mbar_wait(bar_s + s, (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[kTcBC];
+      tmem_ld32(lane_base + s * kTcBC, v);
+      tmem_ld32(lane_base + s * kTcBC + 32, v + 32);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (all_valid) {
+#pragma unroll
+        for (int i = 0; i < kTcBC; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTcBC; ++i)
+          if (i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float mxs = mx * p.scale_log2;
+      float factor = 1.f;
+      bool need = false;
+      if (c == 0) {
+        m_ref = (mx == -INFINITY) ? 0.f : mxs;
+      } else if (mxs > m_ref + kRescaleThreshold) {
+        factor = ex2_approx(m_ref - mxs);
+        m_ref = mxs;
+        l_run *= factor;
+        need = true;
+      }
+      if (c > 0 && __any_sync(0xffffffffu, need)) {
+        // O holds chunks [0, c) once the PV product of chunk c-1 retires; that of chunk c waits for our arrive below.
+        // Parity waits are safe here: bar_s(c) was observed, so the PV product of chunk c-3 (the previous phase of
+        // this barrier) retired long ago -- the barrier is in the phase of chunk c-1 or just past it.
+        mbar_wait(bar_empty + ((c - 1) & 1), ((c - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < HD / 32; ++cc) {
+          uint32_t o[32];
+          tmem_ld32(lane_base + 128 + cc * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st32(lane_base + 128 + cc * 32, o);
+        }
+        tmem_st_wait();
+      }
+      float l_c = 0.f;
+      uint8_t* prow = sP(s) + r * 128;
+      const float neg_m = -m_ref;
+#pragma unroll
+      for (int g = 0; g < kTcBC / 8; ++g) {  // 8 keys -> one 16-byte chunk of the swizzled row
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = g * 8 + 2 * i;
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[kk]), p.scale_log2, neg_m));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[kk + 1]), p.scale_log2, neg_m));
+          if (!all_valid) {
+            p0 = (kk < n_valid) ? p0 : 0.f;
+            p1 = (kk + 1 < n_valid) ? p1 : 0.f;
+          }
+          l_c += p0 + p1;
+          w[i] = pack_bf16(p0, p1);
+        }
+        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l_run += l_c;
+      fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar_p + s);
+    }
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + t_row) * p.ldo + h * HD;
+#pragma unroll 1
+    for (int cc = 0; cc < HD / 32; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(lane_base + 128 + cc * 32, o);
+      tmem_ld_wait();
+      if (t_row >= 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + cc * 32 + g * 8) = w;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, Cfg::kTmemCols);
+  }
+}
+
+template <int HD, bool CAUSAL>
+static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
+                              int B, cudaStream_t st) {
+  using Cfg = AttnTcCfg<HD>;
+  auto kern = attn_tc_kernel<HD, CAUSAL>;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr = true;
+  }
+  dim3 grid((p.T + 127) / 128, p.H, B);
+  const double pairs = CAUSAL ? 0.5 * p.T * (p.T + 1.0) : 1.0 * p.T * p.T;
+  ProfScope prof(kCatFlash, 4.0 * B * p.H * pairs * HD, 2.0 * B * p.H * HD * (4.0 * p.T), st);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Causal prefill, head_dim 128.  q: rotated queries inside the fused qkv buffer [B*T, ld_q] (head h at columns
+// h*128); caches [B, H, Tmax, 128] (rows >= T must be finite); out [B*T, ldo].
+int attn_tc_prefill_launch(const void* q, long long ld_q, const void* kc, const void* vc, void* out, long long ldo, int B,
+                           int H, int T, int Tmax, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  CUtensorMap tq, tk, tv;
+  if (make_tmap_2d(&tq, q, 2, 1LL * B * T, 1LL * H * 128, ld_q, 128)) return -1;
+  if (make_tmap_2d(&tk, kc, 2, 1LL * B * H * Tmax, 128, 128, kTcBC)) return -1;
+  if (make_tmap_2d(&tv, vc, 2, 1LL * B * H * Tmax, 128, 128, kTcBC)) return -1;
+  AttnTcParams p = {};
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.T = T;
+  p.H = H;
+  p.q_col_per_h = 128;
+  p.kv_rows_per_b = H * Tmax;
+  p.kv_rows_per_h = Tmax;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+  return attn_tc_launch_one<128, true>(tq, tk, tv, p, B, st);
+}
+
+// q, k, v packed as [B*T, 3*H*hd] (q | k | v, head h at columns h*hd of each third); head_dim 64 or 128.
+int attn_tc_qkv_launch(const void* qkv, long long ld, void* out, long long ldo, int B, int H, int T, int hd, int causal,
+                       cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (hd != 64 && hd != 128) return set_error("tcgen05 attention: head_dim %d not supported (64 or 128)", hd);
+  const long long D = 1LL * H * hd;
+  CUtensorMap tq, tkv;
+  if (make_tmap_2d(&tq, qkv, 2, 1LL * B * T, 3 * D, ld, 128)) return -1;
+  if (make_tmap_2d(&tkv, qkv, 2, 1LL * B * T, 3 * D, ld, kTcBC)) return -1;
+  AttnTcParams p = {};
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.T = T;
+  p.H = H;
+  p.q_col_per_h = hd;
+  p.kv_rows_per_b = T;
+  p.kv_rows_per_h = 0;
+  p.k_col0 = static_cast<int>(D);
+  p.v_col0 = static_cast<int>(2 * D);
+  p.kv_col_per_h = hd;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
+  if (hd == 64) return causal ? attn_tc_launch_one<64, true>(tq, tkv, tkv, p, B, st)
+                              : attn_tc_launch_one<64, false>(tq, tkv, tkv, p, B, st);
+  return causal ? attn_tc_launch_one<128, true>(tq, tkv, tkv, p, B, st)
+                : attn_tc_launch_one<128, false>(tq, tkv, tkv, p, B, st);
+}
+
+}  // namespace ovla

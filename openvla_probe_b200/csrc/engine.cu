@@ -94,6 +94,7 @@ struct OvlaEngine {
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
+  bool attn_tc = false;   // OVLA_ATTN_TC=1: tcgen05 prefill attention (attention_tc.cu)
   bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -151,6 +152,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   CUDA_TRY(cudaSetDevice(device));
   OvlaEngine* e = new OvlaEngine();
   e->d = *dims;
+  if (const char* tc = getenv("OVLA_ATTN_TC")) e->attn_tc = tc[0] != '0';
   if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
   if (const char* ts = getenv("OVLA_TWO_STREAMS")) e->two_streams = ts[0] != '0';
   if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
@@ -253,6 +255,8 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   W(&e->in_px, B * 3LL * d.n_towers * d.image_size * d.image_size);
   W(&e->out_tokens, 64LL * B);
   if (!rc) rc = cudaMemset(e->err_flag, 0, 16) == cudaSuccess ? 0 : set_error("memset");
+  // cache rows >= T are read (and multiplied by zero probabilities) by the tensor-core prefill attention: keep them finite
+  if (!rc) rc = cudaMemset(e->kv, 0, sizeof(bf16) * e->kv_layer_elems() * d.llm_layers) == cudaSuccess ? 0 : set_error("memset");
   if (rc) {
     std::string msg = last_error();
     ovla_destroy(e);
@@ -482,7 +486,10 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::Vit
     BlockW& b = tw.blocks[i];
     OVLA_TRY(layernorm_launch(v.x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, v.h, D, rows, D, st));
     OVLA_TRY(linear(v.h, D, b.qkv_w, rows, kModeBf16, v.qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
-    OVLA_TRY(flash_attn_launch(v.qkv, v.qkv + D, v.qkv + 2 * D, v.attn, s12, B, w.heads, N, N, hd, 0, st));
+    if (e->attn_tc && hd == 64)
+      OVLA_TRY(attn_tc_qkv_launch(v.qkv, 3LL * D, v.attn, D, B, w.heads, N, hd, 0, st));
+    else
+      OVLA_TRY(flash_attn_launch(v.qkv, v.qkv + D, v.qkv + 2 * D, v.attn, s12, B, w.heads, N, N, hd, 0, st));
     // x = x + ls1(proj(attn))   (in place: each epilogue thread reads its residual before writing)
     OVLA_TRY(linear(v.attn, D, b.proj_w, rows, kModeBf16, v.x, D, b.proj_b.ptr, b.ls1.ptr, v.x, D, 0, 0, st));
     OVLA_TRY(layernorm_launch(v.x, D, b.ln2_w.ptr, b.ln2_b.ptr, 1e-6f, v.h, D, rows, D, st));
@@ -534,7 +541,10 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
                               Tmax, st));
     }
-    OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
+    if (e->attn_tc && hd == 128)
+      OVLA_TRY(attn_tc_prefill_launch(e->l_qkv, 3LL * D, e->k_cache(i), e->v_cache(i), e->l_attn, D, B, H, T, Tmax, st));
+    else
+      OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
     OVLA_TRY(linear(e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));
     OVLA_TRY(linear(e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,

@@ -36,6 +36,12 @@ int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void*
 int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
                       int Tq, int Tk, int head_dim, int causal, cudaStream_t st);
 
+// attention_tc.cu: causal prefill attention on tcgen05 (head_dim 128)
+int attn_tc_prefill_launch(const void* q, long long ld_q, const void* kc, const void* vc, void* out, long long ldo, int B,
+                           int H, int T, int Tmax, cudaStream_t st);
+int attn_tc_qkv_launch(const void* qkv, long long ld, void* out, long long ldo, int B, int H, int T, int hd, int causal,
+                       cudaStream_t st);
+
 // elementwise.cu
 int im2col_launch(const void* px, int B, int c_total, int c0, int H, int W, int patch, int Kpad, void* out,
                   cudaStream_t st);

@@ -165,6 +165,89 @@ def test_flash_attention_vs_oracle(L, B, H, T, hd, causal):
     assert float((got - ref).norm() / ref.norm()) < 6e-3
 
 
+@pytest.mark.parametrize("B,H,T,Tmax,qscale", [(2, 4, 288, 304, 1.0), (3, 2, 25, 64, 1.0), (1, 2, 130, 130, 1.0),
+                                               (2, 3, 128, 128, 1.0), (1, 2, 283, 320, 1.0), (2, 2, 400, 401, 1.0),
+                                               (2, 2, 283, 320, 6.0), (1, 1, 1, 16, 1.0), (1, 2, 700, 704, 3.0)])
+def test_prefill_attention_tcgen05_vs_oracle(L, B, H, T, Tmax, qscale):
+    """tcgen05 causal prefill attention (queries in the fused qkv buffer, K/V in the cache layout [B,H,Tmax,128])
+    against the oracle SDPA, to the same tolerance as the mma.sync kernel; rows >= T of the cache hold other data.
+    qscale > 1 makes the row maxima jump between key chunks, which exercises the lazy O / l rescale in TMEM."""
+    _lib, lib = L
+    hd = 128
+    g = torch.Generator().manual_seed(T * 7 + H)
+    D = H * hd
+    qkv = torch.randn(B, T, 3, H, hd, generator=g)
+    qkv[:, :, 0] *= qscale
+    qkv = bf(qkv)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]           # [B,H,T,hd]
+    ref = O._sdpa(q.float(), k.float(), v.float(), causal=True).permute(0, 2, 1, 3).reshape(B, T, D)
+    buf = qkv.reshape(B * T, 3 * D).contiguous().cuda()
+    kc = bf(torch.randn(B, H, Tmax, hd, generator=g) * 3)                    # finite junk beyond T
+    vc = bf(torch.randn(B, H, Tmax, hd, generator=g) * 3)
+    kc[:, :, :T] = k
+    vc[:, :, :T] = v
+    kcd, vcd = kc.cuda(), vc.cuda()
+    out = torch.zeros(B * T, D, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.ovla_prefill_attention_tc(P(buf), C.c_longlong(3 * D), P(kcd), P(vcd), P(out), C.c_longlong(D),
+                                             B, H, T, Tmax, None))
+    torch.cuda.synchronize()
+    got = out.view(B, T, D).float().cpu()
+    assert float((got - ref).abs().max()) <= 0.006 * float(ref.abs().max()) + 1e-3
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,T,hd,causal,qscale", [(2, 2, 21, 64, 0, 1.0), (1, 16, 261, 64, 0, 1.0), (3, 4, 256, 64, 0, 1.0),
+                                                    (2, 3, 261, 64, 0, 5.0), (2, 2, 130, 64, 1, 1.0),
+                                                    (2, 2, 200, 128, 0, 1.0), (1, 2, 283, 128, 1, 4.0)])
+def test_attention_tcgen05_packed_qkv_vs_oracle(L, B, H, T, hd, causal, qscale):
+    """Same kernel on a packed [B*T, 3D] qkv buffer (the ViT towers' layout), head_dim 64 / 128."""
+    _lib, lib = L
+    g = torch.Generator().manual_seed(T * hd + causal)
+    D = H * hd
+    qkv = torch.randn(B, T, 3, H, hd, generator=g)
+    qkv[:, :, 0] *= qscale
+    qkv = bf(qkv)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    ref = O._sdpa(q.float(), k.float(), v.float(), causal=bool(causal)).permute(0, 2, 1, 3).reshape(B, T, D)
+    buf = qkv.reshape(B * T, 3 * D).contiguous().cuda()
+    out = torch.zeros(B * T, D, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.ovla_attention_tc_qkv(P(buf), C.c_longlong(3 * D), P(out), C.c_longlong(D), B, H, T, hd, causal, None))
+    torch.cuda.synchronize()
+    got = out.view(B, T, D).float().cpu()
+    assert float((got - ref).abs().max()) <= 0.006 * float(ref.abs().max()) + 1e-3
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
+def test_attention_tcgen05_many_waves_deterministic(L):
+    """Llama prefill shape (32 heads, 283 tokens) with enough (batch, head) tiles for many waves of CTAs: every
+    element within 2 bf16 ulps of the fp32 oracle and two launches bit-identical (barrier-phase races show up as rare
+    run-to-run differences)."""
+    _lib, lib = L
+    B, H, T, Tmax, hd = 12, 32, 283, 320, 128
+    D = H * hd
+    g = torch.Generator().manual_seed(5)
+    qkv = bf(torch.randn(B, T, 3, H, hd, generator=g))
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    ref = O._sdpa(q.float(), k.float(), v.float(), causal=True).permute(0, 2, 1, 3).reshape(B * T, D)
+    buf = qkv.reshape(B * T, 3 * D).contiguous().cuda()
+    kc = torch.zeros(B, H, Tmax, hd, dtype=torch.bfloat16)
+    vc = torch.zeros(B, H, Tmax, hd, dtype=torch.bfloat16)
+    kc[:, :, :T] = k
+    vc[:, :, :T] = v
+    kcd, vcd = kc.cuda(), vc.cuda()
+    outs = []
+    for _ in range(3):
+        out = torch.zeros(B * T, D, dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.ovla_prefill_attention_tc(P(buf), C.c_longlong(3 * D), P(kcd), P(vcd), P(out), C.c_longlong(D),
+                                                 B, H, T, Tmax, None))
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    err = (outs[0].float() - ref).abs()
+    assert float(err.max()) <= 2 * 2.0 ** -8 * float(ref.abs().max())
+    assert int((err > 2.0 ** -8 * ref.abs().clamp_min(0.5)).sum()) == 0
+
+
 @pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])
 def test_decode_rope_attention_and_cache_append(L, B, ctx):
     """Fused RoPE + KV append + 1-query attention == oracle llama attention step with a KV cache."""
