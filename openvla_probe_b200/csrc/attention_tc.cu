@@ -69,7 +69,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 struct AttnTcParams {
   __nv_bfloat16* out;
   long long ldo;
-  int T, H;
+  int T, H, n_batch, rot;
   int q_col_per_h;                        // query columns of head h start at h * q_col_per_h
   int kv_rows_per_b, kv_rows_per_h;       // first key row of (b, h) in the K / V tensor maps
   int k_col0, v_col0, kv_col_per_h;       // first column of head h: col0 + h * kv_col_per_h
@@ -106,23 +106,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* bar_empty = bars + 3;   // [2] PV product of the chunk retired: stage (and P) free, O holds chunks [0, c]
   uint64_t* bar_s = bars + 5;       // [2] scores ready in TMEM
   uint64_t* bar_p = bars + 7;       // [2] probabilities in shared memory (128 arrivals)
-  uint64_t* bar_done = bars + 9;    // last PV product retired (single phase: waiters that skipped phases cannot alias)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_done = bars + 9;    // last PV product of the item retired
+  uint64_t* bar_qfree = bars + 10;  // last QK^T product of the item retired: Q may be overwritten
+  uint64_t* bar_ofree = bars + 11;  // the item's O has been read out of TMEM (128 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = gridDim.x;
-  const int tile = n_tiles - 1 - static_cast<int>(blockIdx.x);  // longest (last) tile first
-  const int q0 = p.T - 128 * (n_tiles - tile);                  // may be negative for tile 0: those rows are dropped
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int k_limit = CAUSAL ? q0 + 128 : p.T;                  // keys [0, k_limit); q0 + 128 <= T by construction
-  const int n_chunks = (k_limit + kTcBC - 1) / kTcBC;
-  const int n_last = ((k_limit - (n_chunks - 1) * kTcBC) + 15) & ~15;  // keys issued for the last chunk (16..64)
+  // Persistent CTA: work item w = (batch*H + head) * n_tiles + reversed tile index (longest tile of a head first, the
+  // tiles of one head adjacent so that they run at about the same time on different SMs and share K/V through L2).
+  // Round k hands CTA x the item k*G + (x + k*rot) % G: every round covers a contiguous block of items, and the host
+  // picks `rot` so that a CTA's list walks through all tile lengths (causal tiles cost 1..2*n_tiles-1 chunks): the
+  // static lists then carry equal work.
+  const uint32_t n_tiles = (p.T + 127) / 128;
+  const uint32_t total = n_tiles * p.H * p.n_batch;
+  const uint32_t G = gridDim.x, cta = blockIdx.x;
+  struct Item { int q0, h, b, k_limit, n_chunks, n_last; };
+  auto item_of = [&](uint32_t w) {
+    Item it;
+    const uint32_t bh = w / n_tiles;
+    const int tile = static_cast<int>(n_tiles - 1 - (w - bh * n_tiles));
+    it.b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+    it.h = static_cast<int>(bh - static_cast<uint32_t>(it.b) * p.H);
+    it.q0 = p.T - 128 * (static_cast<int>(n_tiles) - tile);      // negative for tile 0 of a ragged T: rows dropped
+    it.k_limit = CAUSAL ? it.q0 + 128 : p.T;                     // keys [0, k_limit); q0 + 128 <= T by construction
+    it.n_chunks = (it.k_limit + kTcBC - 1) / kTcBC;
+    it.n_last = ((it.k_limit - (it.n_chunks - 1) * kTcBC) + 15) & ~15;  // keys issued for the last chunk (16..64)
+    return it;
+  };
+  auto work = [&](uint32_t k) { return k * G + (cta + k * p.rot) % G; };
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
+    mbar_init(bar_qfree, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full + s, 1);
       mbar_init(bar_empty + s, 1);
@@ -130,6 +148,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(bar_p + s, 128);
     }
     mbar_init(bar_done, 1);
+    mbar_init(bar_ofree, 128);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -141,25 +160,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
+  // `cur` numbers the key chunks this CTA processes across all its items: ring stage cur & 1, phase (cur >> 1) & 1.
   if (warp == 4) {
     // ------------------------------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int q_col = h * p.q_col_per_h, q_row = b * p.T + q0;
-      mbar_expect_tx(bar_q, Cfg::kQBytes);
-#pragma unroll
-      for (int sl = 0; sl < NS; ++sl) tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, q_col + sl * 64, q_row);
-      const int kv_row = b * p.kv_rows_per_b + h * p.kv_rows_per_h;
-      const int k_col = p.k_col0 + h * p.kv_col_per_h, v_col = p.v_col0 + h * p.kv_col_per_h;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c & 1;
-        if (c >= 2) mbar_wait(bar_empty + s, ((c >> 1) - 1) & 1);
-        mbar_expect_tx(bar_full + s, Cfg::kStageBytes);
+      uint32_t cur = 0;
+      for (int k = 0;; ++k) {
+        const uint32_t w = work(k);
+        if (w >= total) break;
+        const Item it = item_of(w);
+        if (k > 0) mbar_wait(bar_qfree, (k - 1) & 1);   // every QK^T product of the previous item has read Q
+        mbar_expect_tx(bar_q, Cfg::kQBytes);
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl)
-          tma_load_2d(&tmap_k, bar_full + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+          tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, it.h * p.q_col_per_h + sl * 64, it.b * p.T + it.q0);
+        const int kv_row = it.b * p.kv_rows_per_b + it.h * p.kv_rows_per_h;
+        const int k_col = p.k_col0 + it.h * p.kv_col_per_h, v_col = p.v_col0 + it.h * p.kv_col_per_h;
+        for (int c = 0; c < it.n_chunks; ++c, ++cur) {
+          const int s = cur & 1;
+          if (cur >= 2) mbar_wait(bar_empty + s, ((cur >> 1) - 1) & 1);
+          mbar_expect_tx(bar_full + s, Cfg::kStageBytes);
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl)
-          tma_load_2d(&tmap_v, bar_full + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+          for (int sl = 0; sl < NS; ++sl)
+            tma_load_2d(&tmap_k, bar_full + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+#pragma unroll
+          for (int sl = 0; sl < NS; ++sl)
+            tma_load_2d(&tmap_v, bar_full + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+        }
       }
     }
   } else if (warp == 5) {
@@ -167,135 +194,158 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(1, 128, 0);                    // N filled in per chunk
       constexpr uint32_t idesc_o = umma_idesc(1, 128, HD) | (1u << 16);      // B (= V) is MN-major
-      mbar_wait(bar_q, 0);
-      for (int c = 0; c <= n_chunks; ++c) {
-        if (c < n_chunks) {
-          const int s = c & 1;
-          const int nc = (c == n_chunks - 1) ? n_last : kTcBC;
-          mbar_wait(bar_full + s, (c >> 1) & 1);
-          tc_fence_after();
-          const uint32_t idesc = idesc_s | (static_cast<uint32_t>(nc >> 3) << 17);
+      uint32_t cur0 = 0;
+      for (int k = 0;; ++k) {
+        const uint32_t w = work(k);
+        if (w >= total) break;
+        const Item it = item_of(w);
+        mbar_wait(bar_q, k & 1);
+        for (int c = 0; c <= it.n_chunks; ++c) {
+          if (c < it.n_chunks) {
+            const uint32_t cur = cur0 + c;
+            const int s = cur & 1;
+            const int nc = (c == it.n_chunks - 1) ? it.n_last : kTcBC;
+            mbar_wait(bar_full + s, (cur >> 1) & 1);
+            tc_fence_after();
+            const uint32_t idesc = idesc_s | (static_cast<uint32_t>(nc >> 3) << 17);
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks) {
-            const uint64_t a = umma_desc_sw128(smem_u32(sQ + (ks >> 2) * kSlabQ)) + 2 * (ks & 3);
-            const uint64_t bd = umma_desc_sw128(smem_u32(sK(s) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
-            umma_bf16<1>(tmem + s * kTcBC, a, bd, idesc, ks != 0);
+            for (int ks = 0; ks < HD / 16; ++ks) {
+              const uint64_t a = umma_desc_sw128(smem_u32(sQ + (ks >> 2) * kSlabQ)) + 2 * (ks & 3);
+              const uint64_t bd = umma_desc_sw128(smem_u32(sK(s) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
+              umma_bf16<1>(tmem + s * kTcBC, a, bd, idesc, ks != 0);
+            }
+            umma_commit(bar_s + s);
+            if (c == it.n_chunks - 1) umma_commit(bar_qfree);
           }
-          umma_commit(bar_s + s);
-        }
-        if (c > 0) {
-          const int cp = c - 1, s = cp & 1;
-          const int nc = (cp == n_chunks - 1) ? n_last : kTcBC;
-          mbar_wait(bar_p + s, (cp >> 1) & 1);
-          tc_fence_after();
-          for (int j = 0; j < nc / 16; ++j) {
-            const uint64_t a = umma_desc_sw128(smem_u32(sP(s))) + 2 * j;
-            const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(s) + j * 16 * 128), kSlabKV);
-            umma_bf16<1>(tmem + 128, a, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
+          if (c > 0) {
+            const int cp = c - 1;
+            const uint32_t cur = cur0 + cp;
+            const int s = cur & 1;
+            const int nc = (cp == it.n_chunks - 1) ? it.n_last : kTcBC;
+            mbar_wait(bar_p + s, (cur >> 1) & 1);
+            if (cp == 0 && k > 0) mbar_wait(bar_ofree, (k - 1) & 1);   // the previous item's O has been read out
+            tc_fence_after();
+            for (int j = 0; j < nc / 16; ++j) {
+              const uint64_t a = umma_desc_sw128(smem_u32(sP(s))) + 2 * j;
+              const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(s) + j * 16 * 128), kSlabKV);
+              umma_bf16<1>(tmem + 128, a, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + s);
+            if (cp == it.n_chunks - 1) umma_commit(bar_done);
           }
-          umma_commit(bar_empty + s);
-          if (cp == n_chunks - 1) umma_commit(bar_done);
         }
+        cur0 += it.n_chunks;
       }
     }
   } else {
     // ------------------------------------------------------------------------------------------ softmax: thread = row
     const int r = tid;
-    const int t_row = q0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    float m_ref = 0.f, l_run = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c & 1;
-      const int key0 = c * kTcBC;
-      int n_valid = k_limit - key0;
-      if (CAUSAL) n_valid = max(0, min(n_valid, t_row - key0 + 1));
-      const bool all_valid = __all_sync(0xffffffffu, n_valid >= kTcBC);
-      mbar_wait(bar_s + s, (c >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[kTcBC];
-      tmem_ld32(lane_base + s * kTcBC, v);
-      tmem_ld32(lane_base + s * kTcBC + 32, v + 32);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-      if (all_valid) {
-#pragma unroll
-        for (int i = 0; i < kTcBC; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < kTcBC; ++i)
-          if (i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      const float mxs = mx * p.scale_log2;
-      float factor = 1.f;
-      bool need = false;
-      if (c == 0) {
-        m_ref = (mx == -INFINITY) ? 0.f : mxs;
-      } else if (mxs > m_ref + kRescaleThreshold) {
-        factor = ex2_approx(m_ref - mxs);
-        m_ref = mxs;
-        l_run *= factor;
-        need = true;
-      }
-      if (c > 0 && __any_sync(0xffffffffu, need)) {
-        // O holds chunks [0, c) once the PV product of chunk c-1 retires; that of chunk c waits for our arrive below.
-        // Parity waits are safe here: bar_s(c) was observed, so the PV product of chunk c-3 (the previous phase of
-        // this barrier) retired long ago -- the barrier is in the phase of chunk c-1 or just past it.
-        mbar_wait(bar_empty + ((c - 1) & 1), ((c - 1) >> 1) & 1);
+    uint32_t cur = 0;
+    for (int k = 0;; ++k) {
+      const uint32_t w = work(k);
+      if (w >= total) break;
+      const Item it = item_of(w);
+      const int t_row = it.q0 + r;
+      float m_ref = 0.f, l_run = 0.f;
+      for (int c = 0; c < it.n_chunks; ++c, ++cur) {
+        const int s = cur & 1;
+        const int key0 = c * kTcBC;
+        int n_valid = it.k_limit - key0;
+        if (CAUSAL) n_valid = max(0, min(n_valid, t_row - key0 + 1));
+        const bool all_valid = __all_sync(0xffffffffu, n_valid >= kTcBC);
+        mbar_wait(bar_s + s, (cur >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < HD / 32; ++cc) {
-          uint32_t o[32];
-          tmem_ld32(lane_base + 128 + cc * 32, o);
-          tmem_ld_wait();
+        uint32_t v[kTcBC];
+        tmem_ld32(lane_base + s * kTcBC, v);
+        tmem_ld32(lane_base + s * kTcBC + 32, v + 32);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+        if (all_valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-          tmem_st32(lane_base + 128 + cc * 32, o);
+          for (int i = 0; i < kTcBC; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTcBC; ++i)
+            if (i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
-        tmem_st_wait();
-      }
-      float l_c = 0.f;
-      uint8_t* prow = sP(s) + r * 128;
-      const float neg_m = -m_ref;
+        const float mxs = mx * p.scale_log2;
+        float factor = 1.f;
+        bool need = false;
+        if (c == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mxs;
+        } else if (mxs > m_ref + kRescaleThreshold) {
+          factor = ex2_approx(m_ref - mxs);
+          m_ref = mxs;
+          l_run *= factor;
+          need = true;
+        }
+        if (c > 0 && __any_sync(0xffffffffu, need)) {
+          // O holds chunks [0, c) once the PV product of chunk c-1 retires; that of chunk c waits for our arrive below.
+          // A parity wait is safe although most chunks skip it: bar_s of this chunk was observed, so the PV product
+          // two phases back on this barrier (chunk cur-3) retired long ago -- the barrier is in the phase of chunk
+          // cur-1 or just past it.
+          mbar_wait(bar_empty + ((cur - 1) & 1), ((cur - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < HD / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + 128 + cc * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < kTcBC / 8; ++g) {  // 8 keys -> one 16-byte chunk of the swizzled row
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = g * 8 + 2 * i;
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[kk]), p.scale_log2, neg_m));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[kk + 1]), p.scale_log2, neg_m));
-          if (!all_valid) {
-            p0 = (kk < n_valid) ? p0 : 0.f;
-            p1 = (kk + 1 < n_valid) ? p1 : 0.f;
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st32(lane_base + 128 + cc * 32, o);
           }
-          l_c += p0 + p1;
-          w[i] = pack_bf16(p0, p1);
+          tmem_st_wait();
         }
-        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      l_run += l_c;
-      fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(bar_p + s);
-    }
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + t_row) * p.ldo + h * HD;
-#pragma unroll 1
-    for (int cc = 0; cc < HD / 32; ++cc) {
-      uint32_t o[32];
-      tmem_ld32(lane_base + 128 + cc * 32, o);
-      tmem_ld_wait();
-      if (t_row >= 0) {
+        float l_c = 0.f;
+        uint8_t* prow = sP(s) + r * 128;
+        const float neg_m = -m_ref;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-          w.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-          w.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-          w.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + cc * 32 + g * 8) = w;
+        for (int g = 0; g < kTcBC / 8; ++g) {  // 8 keys -> one 16-byte chunk of the swizzled row
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = g * 8 + 2 * i;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[kk]), p.scale_log2, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[kk + 1]), p.scale_log2, neg_m));
+            if (!all_valid) {
+              p0 = (kk < n_valid) ? p0 : 0.f;
+              p1 = (kk + 1 < n_valid) ? p1 : 0.f;
+            }
+            l_c += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_run += l_c;
+        fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(bar_p + s);
+      }
+      mbar_wait(bar_done, k & 1);   // waited every item, so the parity cannot alias
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.T + t_row) * p.ldo + it.h * HD;
+#pragma unroll 1
+      for (int cc = 0; cc < HD / 32; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(lane_base + 128 + cc * 32, o);
+        tmem_ld_wait();
+        if (cc == HD / 32 - 1) {   // O is in registers: the next item's first PV product may overwrite it
+          tc_fence_before();
+          mbar_arrive(bar_ofree);
+        }
+        if (t_row >= 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            o4.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            o4.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            o4.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + cc * 32 + g * 8) = o4;
+          }
         }
       }
     }
@@ -318,10 +368,19 @@ static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, cons
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr = true;
   }
-  dim3 grid((p.T + 127) / 128, p.H, B);
+  AttnTcParams pp = p;
+  pp.n_batch = B;
+  const long long total = 1LL * ((p.T + 127) / 128) * p.H * B;
+  int grid_x = 2 * num_sms();   // two resident CTAs per SM
+  if (const char* gx = getenv("OVLA_ATTN_TC_GRID")) grid_x = atoi(gx) > 0 ? atoi(gx) : grid_x;
+  const dim3 grid(static_cast<unsigned>(total < grid_x ? total : grid_x));
+  const int n_tiles = (p.T + 127) / 128;
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  pp.rot = 0;   // kind of CTA x's k-th item ~ (x + k * (G + rot)) mod n_tiles: make the step coprime with n_tiles
+  while (n_tiles > 1 && gcd((static_cast<int>(grid.x) + pp.rot) % n_tiles, n_tiles) != 1) ++pp.rot;
   const double pairs = CAUSAL ? 0.5 * p.T * (p.T + 1.0) : 1.0 * p.T * p.T;
   ProfScope prof(kCatFlash, 4.0 * B * p.H * pairs * HD, 2.0 * B * p.H * HD * (4.0 * p.T), st);
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, pp);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
