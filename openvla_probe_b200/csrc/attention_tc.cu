@@ -1,23 +1,26 @@
 // tcgen05 / TMEM flash attention: the causal Llama prefill (head_dim 128, K/V in the cache layout) and the
 // non-causal head_dim-64 ViT tower (q, k, v packed in one [B*T, 3D] buffer).
 //
-// One CTA = 128 query rows of one (batch, head); keys are consumed in chunks of 64 with an online softmax.
-//   warp 4      TMA producer: Q tile once, then K/V chunks into a 2-stage ring (128B-swizzled)
+// A work item = 128 query rows of one (batch, head); keys are consumed in chunks of 64 with an online softmax.
+// CTAs are persistent (two per SM) and walk a static, cost-balanced list of items.
+//   warp 4      TMA producer: Q tile per item, K chunks and V chunks into two separate rings (128B-swizzled)
 //   warp 5      MMA issuer:   S_c[128 x 64]  = Q . K_c^T   (SS, both K-major)            -> TMEM cols [64*(c&1), +64)
-//                             O  [128 x HD] += P_c . V_c   (V as an MN-major B operand, i.e. exactly as it lies in
-//                                                           memory: [key][hd])            -> TMEM cols [128, 128+HD)
+//                             O  [128 x HD] += P_c . V_c   (TS: P_c read from TMEM; V as an MN-major B operand, i.e.
+//                                                           exactly as it lies in memory) -> TMEM cols [128, 128+HD)
 //               S_{c+1} is issued before the PV product of chunk c, so the tensor core computes the next scores
 //               while the softmax warps work on the current ones.
 //   warps 0-3   softmax: thread r owns query row r (= TMEM lane r): tcgen05.ld the 64 scores, mask, p = exp2(..),
-//               P_c -> bf16 into shared memory in the K-major 128B-swizzle layout the tensor core reads.
+//               P_c -> packed bf16 written back with tcgen05.st over the first 32 columns of S_c.
+// Neither S nor P ever touches shared memory, so a K stage is free as soon as its QK^T product retires and the rings
+// run two to three chunks ahead of the tensor core (the L2 / HBM latency of a chunk is ~2 chunk times).
 // O accumulates in TMEM across chunks.  The running max is only refreshed (and O, l rescaled with a TMEM
 // load-multiply-store) when a row's max grows by more than 2^8 relative to the reference it is using, so the rescale
 // is rare; probabilities are bounded by 256 in that frame, which bf16 and the fp32 accumulators hold exactly as well
 // as values <= 1.  Probabilities are rounded to bf16 before the PV product, as flash-attn does.
 // Tiles are aligned to the END of the sequence (the ragged tile is the first one, which under the causal mask has the
 // fewest keys), and the last chunk of a tile is shortened to a multiple of 16 keys.
-// head_dim 128: P_c is written over K_c (dead once S_c is complete) -> 96 KB of shared memory, 256 TMEM columns:
-// two CTAs per SM.  head_dim 64: 80 KB with separate P buffers.
+// head_dim 128: Q 32 KB + 3 K stages + 2 V stages of 16 KB = 112 KB and 256 TMEM columns: two CTAs per SM.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "host_util.h"
@@ -79,14 +82,27 @@ struct AttnTcParams {
 template <int HD>
 struct AttnTcCfg {
   static constexpr int kNS = HD / 64;                       // 64-column slabs per operand
-  static constexpr bool kAliasP = (HD == 128);              // P_c overwrites K_c
+  static constexpr int kNK = HD == 128 ? 3 : 4;             // K ring depth
+  static constexpr int kNV = HD == 128 ? 2 : 4;             // V ring depth
   static constexpr int kQBytes = kNS * kSlabQ;
-  static constexpr int kStageBytes = 2 * kNS * kSlabKV;     // K chunk + V chunk
-  static constexpr int kPOff = kQBytes + 2 * kStageBytes;
-  static constexpr int kBarOff = kPOff + (kAliasP ? 0 : 2 * kSlabQ);
-  static constexpr int kSmemBytes = kBarOff + 128 + 1024;   // + barriers + alignment slack
-  static constexpr int kTmemCols = 256;                     // S ping-pong [0,128) | O [128, 128+HD)
+  static constexpr int kChunkBytes = kNS * kSlabKV;         // one K (or V) chunk
+  static constexpr int kKOff = kQBytes;
+  static constexpr int kVOff = kKOff + kNK * kChunkBytes;
+  static constexpr int kBarOff = kVOff + kNV * kChunkBytes;
+  static constexpr int kSmemBytes = kBarOff + 256;          // + barriers; the base must be 1024-byte aligned (checked)
+  static constexpr int kTmemCols = 256;                     // S/P ping-pong [0,128) | O [128, 128+HD)
+  static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 };
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = packed bf16 pairs, row r in lane r, 8 columns per K = 16 step
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(kTcThreads, 2)
@@ -94,22 +110,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
   using Cfg = AttnTcCfg<HD>;
   constexpr int NS = Cfg::kNS;
-  extern __shared__ uint8_t smem_raw_tc[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  constexpr int NK = Cfg::kNK, NV = Cfg::kNV;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023)) {
+    printf("attn_tc_kernel: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
-  auto sK = [&](int s) { return smem + Cfg::kQBytes + s * Cfg::kStageBytes; };
-  auto sV = [&](int s) { return smem + Cfg::kQBytes + s * Cfg::kStageBytes + NS * kSlabKV; };
-  auto sP = [&](int s) { return Cfg::kAliasP ? sK(s) : smem + Cfg::kPOff + s * kSlabQ; };
+  auto sK = [&](int s) { return smem + Cfg::kKOff + s * Cfg::kChunkBytes; };
+  auto sV = [&](int s) { return smem + Cfg::kVOff + s * Cfg::kChunkBytes; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_full = bars + 1;    // [2] K/V chunk landed
-  uint64_t* bar_empty = bars + 3;   // [2] PV product of the chunk retired: stage (and P) free, O holds chunks [0, c]
-  uint64_t* bar_s = bars + 5;       // [2] scores ready in TMEM
-  uint64_t* bar_p = bars + 7;       // [2] probabilities in shared memory (128 arrivals)
-  uint64_t* bar_done = bars + 9;    // last PV product of the item retired
-  uint64_t* bar_qfree = bars + 10;  // last QK^T product of the item retired: Q may be overwritten
-  uint64_t* bar_ofree = bars + 11;  // the item's O has been read out of TMEM (128 arrivals)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_q = bars + 0;       // Q tile landed
+  uint64_t* bar_qfree = bars + 1;   // last QK^T product of the item retired: Q may be overwritten
+  uint64_t* bar_done = bars + 2;    // last PV product of the item retired
+  uint64_t* bar_ofree = bars + 3;   // the item's O has been read out of TMEM (128 arrivals)
+  uint64_t* bar_s = bars + 4;       // [2] scores ready in TMEM
+  uint64_t* bar_p = bars + 6;       // [2] probabilities written back to TMEM (128 arrivals)
+  uint64_t* bar_kfull = bars + 8;   // [NK] K chunk landed
+  uint64_t* bar_kfree = bars + 12;  // [NK] its QK^T product retired
+  uint64_t* bar_vfull = bars + 16;  // [NV] V chunk landed
+  uint64_t* bar_vfree = bars + 20;  // [NV] its PV product retired (O holds chunks up to and including it)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Persistent CTA: work item w = (batch*H + head) * n_tiles + reversed tile index (longest tile of a head first, the
@@ -142,10 +163,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     mbar_init(bar_q, 1);
     mbar_init(bar_qfree, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + s, 1);
-      mbar_init(bar_empty + s, 1);
       mbar_init(bar_s + s, 1);
       mbar_init(bar_p + s, 128);
+    }
+    for (int s = 0; s < NK; ++s) {
+      mbar_init(bar_kfull + s, 1);
+      mbar_init(bar_kfree + s, 1);
+    }
+    for (int s = 0; s < NV; ++s) {
+      mbar_init(bar_vfull + s, 1);
+      mbar_init(bar_vfree + s, 1);
     }
     mbar_init(bar_done, 1);
     mbar_init(bar_ofree, 128);
@@ -160,11 +187,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
-  // `cur` numbers the key chunks this CTA processes across all its items: ring stage cur & 1, phase (cur >> 1) & 1.
+  // `cur` numbers the key chunks this CTA processes across all its items; ring stage = cur % depth,
+  // phase = (cur / depth) & 1.
   if (warp == 4) {
     // ------------------------------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t cur = 0;
+      uint32_t cur0 = 0;
       for (int k = 0;; ++k) {
         const uint32_t w = work(k);
         if (w >= total) break;
@@ -176,17 +204,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, it.h * p.q_col_per_h + sl * 64, it.b * p.T + it.q0);
         const int kv_row = it.b * p.kv_rows_per_b + it.h * p.kv_rows_per_h;
         const int k_col = p.k_col0 + it.h * p.kv_col_per_h, v_col = p.v_col0 + it.h * p.kv_col_per_h;
-        for (int c = 0; c < it.n_chunks; ++c, ++cur) {
-          const int s = cur & 1;
-          if (cur >= 2) mbar_wait(bar_empty + s, ((cur >> 1) - 1) & 1);
-          mbar_expect_tx(bar_full + s, Cfg::kStageBytes);
+        auto load_k = [&](int c) {
+          const uint32_t cur = cur0 + c, s = cur % NK;
+          if (cur >= NK) mbar_wait(bar_kfree + s, (cur / NK - 1) & 1);
+          mbar_expect_tx(bar_kfull + s, Cfg::kChunkBytes);
 #pragma unroll
           for (int sl = 0; sl < NS; ++sl)
-            tma_load_2d(&tmap_k, bar_full + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+            tma_load_2d(&tmap_k, bar_kfull + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+        };
+        auto load_v = [&](int c) {
+          const uint32_t cur = cur0 + c, s = cur % NV;
+          if (cur >= NV) mbar_wait(bar_vfree + s, (cur / NV - 1) & 1);
+          mbar_expect_tx(bar_vfull + s, Cfg::kChunkBytes);
 #pragma unroll
           for (int sl = 0; sl < NS; ++sl)
-            tma_load_2d(&tmap_v, bar_full + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+            tma_load_2d(&tmap_v, bar_vfull + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+        };
+        // K runs one chunk ahead of V: the order of the waits then matches the order in which the products retire
+        load_k(0);
+        for (int c = 0; c < it.n_chunks; ++c) {
+          if (c + 1 < it.n_chunks) load_k(c + 1);
+          load_v(c);
         }
+        cur0 += it.n_chunks;
       }
     }
   } else if (warp == 5) {
@@ -205,15 +245,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const uint32_t cur = cur0 + c;
             const int s = cur & 1;
             const int nc = (c == it.n_chunks - 1) ? it.n_last : kTcBC;
-            mbar_wait(bar_full + s, (cur >> 1) & 1);
+            mbar_wait(bar_kfull + cur % NK, (cur / NK) & 1);
             tc_fence_after();
             const uint32_t idesc = idesc_s | (static_cast<uint32_t>(nc >> 3) << 17);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks) {
               const uint64_t a = umma_desc_sw128(smem_u32(sQ + (ks >> 2) * kSlabQ)) + 2 * (ks & 3);
-              const uint64_t bd = umma_desc_sw128(smem_u32(sK(s) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
+              const uint64_t bd = umma_desc_sw128(smem_u32(sK(cur % NK) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
               umma_bf16<1>(tmem + s * kTcBC, a, bd, idesc, ks != 0);
             }
+            umma_commit(bar_kfree + cur % NK);
             umma_commit(bar_s + s);
             if (c == it.n_chunks - 1) umma_commit(bar_qfree);
           }
@@ -222,15 +263,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const uint32_t cur = cur0 + cp;
             const int s = cur & 1;
             const int nc = (cp == it.n_chunks - 1) ? it.n_last : kTcBC;
+            mbar_wait(bar_vfull + cur % NV, (cur / NV) & 1);
             mbar_wait(bar_p + s, (cur >> 1) & 1);
             if (cp == 0 && k > 0) mbar_wait(bar_ofree, (k - 1) & 1);   // the previous item's O has been read out
             tc_fence_after();
             for (int j = 0; j < nc / 16; ++j) {
-              const uint64_t a = umma_desc_sw128(smem_u32(sP(s))) + 2 * j;
-              const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(s) + j * 16 * 128), kSlabKV);
-              umma_bf16<1>(tmem + 128, a, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
+              const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(cur % NV) + j * 16 * 128), kSlabKV);
+              umma_bf16_ts(tmem + 128, tmem + s * kTcBC + 8 * j, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
             }
-            umma_commit(bar_empty + s);
+            umma_commit(bar_vfree + cur % NV);
             if (cp == it.n_chunks - 1) umma_commit(bar_done);
           }
         }
@@ -285,7 +326,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           // A parity wait is safe although most chunks skip it: bar_s of this chunk was observed, so the PV product
           // two phases back on this barrier (chunk cur-3) retired long ago -- the barrier is in the phase of chunk
           // cur-1 or just past it.
-          mbar_wait(bar_empty + ((cur - 1) & 1), ((cur - 1) >> 1) & 1);
+          mbar_wait(bar_vfree + (cur - 1) % NV, ((cur - 1) / NV) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < HD / 32; ++cc) {
@@ -299,27 +340,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tmem_st_wait();
         }
         float l_c = 0.f;
-        uint8_t* prow = sP(s) + r * 128;
         const float neg_m = -m_ref;
+        uint32_t pk[kTcBC / 2];
 #pragma unroll
-        for (int g = 0; g < kTcBC / 8; ++g) {  // 8 keys -> one 16-byte chunk of the swizzled row
-          uint32_t pk[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int kk = g * 8 + 2 * i;
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[kk]), p.scale_log2, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[kk + 1]), p.scale_log2, neg_m));
-            if (!all_valid) {
-              p0 = (kk < n_valid) ? p0 : 0.f;
-              p1 = (kk + 1 < n_valid) ? p1 : 0.f;
-            }
-            l_c += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
+        for (int i = 0; i < kTcBC / 2; ++i) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
+          if (!all_valid) {
+            p0 = (2 * i < n_valid) ? p0 : 0.f;
+            p1 = (2 * i + 1 < n_valid) ? p1 : 0.f;
           }
-          *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          l_c += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
         }
         l_run += l_c;
-        fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        tmem_st32(lane_base + s * kTcBC, pk);   // P_c over the first half of S_c (already in registers)
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_p + s);
       }
@@ -366,6 +402,7 @@ static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, cons
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   AttnTcParams pp = p;

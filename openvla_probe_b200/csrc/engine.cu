@@ -94,7 +94,7 @@ struct OvlaEngine {
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
-  bool attn_tc = false;   // OVLA_ATTN_TC=1: tcgen05 prefill attention (attention_tc.cu)
+  bool attn_tc = true;    // OVLA_ATTN_TC=0 falls back to the mma.sync flash kernel for head_dim 64 / 128 (A/B runs)
   bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
