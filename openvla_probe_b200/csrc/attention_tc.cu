@@ -44,6 +44,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two lanes of work per issue slot
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -295,21 +315,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         int n_valid = it.k_limit - key0;
         if (CAUSAL) n_valid = max(0, min(n_valid, t_row - key0 + 1));
         const bool all_valid = __all_sync(0xffffffffu, n_valid >= kTcBC);
+        const bool none_valid = __all_sync(0xffffffffu, n_valid <= 0 || t_row < 0);
         mbar_wait(bar_s + s, (cur >> 1) & 1);
         tc_fence_after();
+        if (none_valid) {
+          // this warp's 32 rows see none of the chunk's keys (above the causal diagonal) or are all dropped rows of a
+          // ragged first tile: P = 0, nothing to accumulate
+          uint32_t z[kTcBC / 2];
+#pragma unroll
+          for (int i = 0; i < kTcBC / 2; ++i) z[i] = 0u;
+          tmem_st32(lane_base + s * kTcBC, z);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_p + s);
+          continue;
+        }
         uint32_t v[kTcBC];
         tmem_ld32(lane_base + s * kTcBC, v);
         tmem_ld32(lane_base + s * kTcBC + 32, v + 32);
         tmem_ld_wait();
-        float mx = -INFINITY;
-        if (all_valid) {
+        if (!all_valid) {   // warp-uniform: only warps that straddle the diagonal / the end of the sequence pay this
 #pragma unroll
-          for (int i = 0; i < kTcBC; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < kTcBC; ++i)
-            if (i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < kTcBC; ++i) v[i] = (i < n_valid) ? v[i] : 0xff800000u;   // -inf -> p = 0
         }
+        float mx = __uint_as_float(v[0]);
+#pragma unroll
+        for (int i = 1; i < kTcBC; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
         const float mxs = mx * p.scale_log2;
         float factor = 1.f;
         bool need = false;
@@ -339,21 +370,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           tmem_st_wait();
         }
-        float l_c = 0.f;
-        const float neg_m = -m_ref;
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(-m_ref, -m_ref);
+        uint64_t l2 = pack_f32x2(0.f, 0.f);
         uint32_t pk[kTcBC / 2];
 #pragma unroll
         for (int i = 0; i < kTcBC / 2; ++i) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
-          if (!all_valid) {
-            p0 = (2 * i < n_valid) ? p0 : 0.f;
-            p1 = (2 * i + 1 < n_valid) ? p1 : 0.f;
-          }
-          l_c += p0 + p1;
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          l2 = add_f32x2(l2, pack_f32x2(p0, p1));
           pk[i] = pack_bf16(p0, p1);
         }
-        l_run += l_c;
+        float l_lo, l_hi;
+        unpack_f32x2(l2, l_lo, l_hi);
+        l_run += l_lo + l_hi;
         tmem_st32(lane_base + s * kTcBC, pk);   // P_c over the first half of S_c (already in registers)
         tmem_st_wait();
         tc_fence_before();
