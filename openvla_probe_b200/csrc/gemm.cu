@@ -125,6 +125,17 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (g_split == -2) { const char* ev = getenv("OVLA_SPLITK"); g_split = ev ? atoi(ev) : -1; }  // -1 auto, 0/1 off, n forced
   const int group = g_group > 0 ? g_group : ((N <= 4096 && K <= 4096) ? 8 : 16);
 
+  // L2 eviction hints: OVLA_GEMM_L2 = two letters for the A and W tile loads, n(ormal) / f(irst) / l(ast)
+  static unsigned long long g_l2[2] = {0, 0};
+  if (!g_l2[0]) {
+    const char* ev = getenv("OVLA_GEMM_L2");
+    for (int i = 0; i < 2; ++i) {
+      const char c = (ev && ev[0] && ev[1]) ? ev[i] : 'n';
+      g_l2[i] = c == 'l' ? kL2EvictLast : c == 'f' ? kL2EvictFirst : kL2EvictNormal;
+    }
+  }
+  const unsigned long long l2_a = g_l2[0], l2_b = g_l2[1];
+
   // split-K for the small-M weight-streaming shapes (see splitk.cu)
   const int num_k = (K + (128 / eb) - 1) / (128 / eb);
   int split = 1;
@@ -161,7 +172,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (make_tmap_2d(&tb, W, eb, N, K, ldw, bn / cg)) return -1;
   if (split >= 2) {
     const int kps = (num_k + split - 1) / split;
-    GemmShape s{M, N, K, group, split, kps};
+    GemmShape s{M, N, K, group, split, kps, l2_a, l2_b};
     GemmEpi pe = {};
     pe.out = splitk_workspace();
     pe.ldo = N;
@@ -169,7 +180,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, s, pe, num_sms, stream)));
     return splitk_epilogue_launch(mode, splitk_workspace(), 1LL * M * N, N, split, M, N, epi, stream);
   }
-  GemmShape s{M, N, K, group, 1, num_k};
+  GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b};
   if (kind == kKindBf16) {
     if (mode == kModeBf16) return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
     if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);

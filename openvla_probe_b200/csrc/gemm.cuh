@@ -52,6 +52,7 @@ struct GemmShape {
   int group_m;  // rasterisation group size (row-tiles)
   int split_k;  // K slices (each tile of a slice accumulates kb_per_split K blocks); 1 = no split
   int kb_per_split;
+  unsigned long long l2_a, l2_b;  // L2 eviction-priority hints of the A / W tile loads (kL2Evict*)
 };
 
 static constexpr int kGemmThreads = 384;
@@ -153,12 +154,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sb = sa + kStageABytes;
           if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a);
-            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b);
+            tma_load_2d_hint(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a, shape.l2_a);
+            tma_load_2d_hint(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, shape.l2_b);
           } else {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a);
-            tma_load_2d_pair(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b);
+            tma_load_2d_pair_hint(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a, shape.l2_a);
+            tma_load_2d_pair_hint(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, shape.l2_b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }

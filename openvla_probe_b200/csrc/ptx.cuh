@@ -107,6 +107,27 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same loads with an L2 eviction-priority hint (createpolicy encodings, as in CUTLASS' TMA::CacheHintSm90)
+static constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull;
+static constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;
+static constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                 unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                      unsigned long long policy) {
+  uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"

@@ -32,7 +32,13 @@ def child():
     print("RESULT " + json.dumps({"ms_per_layer": round(ms, 3), "tflops": round(fl / ms / 1e9, 1)}))
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1: child(); sys.exit(0)
+    if sys.argv[1:] == ["child"]: child(); sys.exit(0)
+    if sys.argv[1:] == ["l2"]:
+        for hint in ("nn", "ln", "lf", "nf", "ll", "nn", "ln"):
+            r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, OVLA_GEMM_L2=hint), capture_output=True, text=True, timeout=200)
+            line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            print(json.dumps({"l2_hint_a_w": hint, "res": json.loads(line[-1][7:]) if line else r.stderr[-300:]}), flush=True)
+        sys.exit(0)
     for g in (8, 4, 16, 32, 8, 16):
         r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, OVLA_GEMM_GROUP=str(g)), capture_output=True, text=True, timeout=200)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]

@@ -3,7 +3,7 @@
 # 1) plain runs must exit 0; 2) per-launch device times of one whole bs=256 step; 3) --set full of the top kernels;
 # 4) bs=1 decode kernels (GEMV, fused decode attention) with CUDA graphs disabled so that ncu sees plain launches.
 R=${1:-r01}
-N=${2:-1983}
+N=${2:-2367}
 CMD="python bench.py --steps 1 --warmup 1 --lite"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${R}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${R}_plain.log; exit 1; }
@@ -13,8 +13,10 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 
     -o gpurun_out/${R}_gemm -f $CMD > gpurun_out/${R}_ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:decode_rope_attn -s 4 -c 2 \
     -o gpurun_out/${R}_decode_attn -f $CMD > gpurun_out/${R}_ncu_decode.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:flash_attn -s 60 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:flash_attn -s 10 -c 1 \
     -o gpurun_out/${R}_flash_attn -f $CMD > gpurun_out/${R}_ncu_flash.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 26 -c 2 \
+    -o gpurun_out/${R}_attn_tc -f $CMD > gpurun_out/${R}_ncu_attn_tc.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:norm_rows -s 120 -c 2 \
     -o gpurun_out/${R}_norm -f $CMD > gpurun_out/${R}_ncu_norm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pool_tokens -s 3 -c 1 \
