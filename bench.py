@@ -57,8 +57,10 @@ def ncu_traffic():
     """DRAM bytes per launch of the largest GEMM instance of the step (Llama gate_up, SwiGLU epilogue: 32 % of the
     step), from the committed `ncu --set full` capture; None when the summary is not in the tree."""
     import csv
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_ncu_gemm_summary.csv")
+    import glob
+    cands = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_ncu_gemm_summary.csv")))
     try:
+        path = cands[-1]
         rows = list(csv.reader(open(path)))
         hdr = rows[0]
         ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
@@ -66,8 +68,9 @@ def ncu_traffic():
             if "<256, 2, 1, 0>" in r[ik]:
                 return (float(r[ir]) + float(r[iw])) * 1e9, (
                     "bytes per launch of gemm_tcgen05_kernel<256,2,SwiGLU> (M=72448 N=22016 K=4096; algorithmic 2.37e9: "
-                    "A 0.59 + W 0.18 + out 1.59 GB) from profiles/r01b_ncu_gemm_summary.csv; the excess is A/W tile "
-                    "re-reads that miss L2, at 1.4 TB/s -- 22 % of HBM peak, not the limiter of this tensor-bound kernel")
+                    "A 0.59 + W 0.18 + out 1.59 GB) from profiles/" + os.path.basename(path) + "; the excess is A/W tile "
+                    "re-reads that miss L2, at ~1.1-1.4 TB/s -- about a fifth of HBM peak, not the limiter of this "
+                    "tensor-bound kernel (L2 eviction hints did not change its time: profiles/r01_gemm_l2_hint_sweep.jsonl)")
     except (OSError, ValueError, IndexError):
         pass
     return None, "no ncu capture in profiles/"
