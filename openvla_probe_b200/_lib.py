@@ -5,9 +5,12 @@ There is no CPU or PyTorch fallback: if the shared library is missing or a call 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "libovla_b200.so"
+if os.environ.get("OVLA_B200_LIB"):  # A/B runs of two builds of the same library inside one process tree
+    _LIB_PATH = Path(os.environ["OVLA_B200_LIB"])
 _lib = None
 
 

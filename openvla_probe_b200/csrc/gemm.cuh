@@ -218,66 +218,85 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       if constexpr (MODE == kModeBf16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
-        const __nv_bfloat16* res = epi.resid ? epi.resid + static_cast<long long>(row) * epi.ldr : nullptr;
+        const __nv_bfloat16* res = (epi.resid && row_ok) ? epi.resid + static_cast<long long>(row) * epi.ldr : nullptr;
+        // The residual row segment of a chunk (64 B per thread, rows a full pitch apart) is fetched one chunk ahead:
+        // issued back to back with the accumulator wait these loads cost ~1 us each and, with short K (the ViT
+        // proj / fc2 GEMMs), made the epilogue longer than the next tile's main loop.
+        uint4 rr[4] = {};
+        auto fetch_resid = [&](int c, uint4* dst) {
+          const int col = col0 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (res && c < BN / 32 && col + g * 8 < shape.N) dst[g] = *reinterpret_cast<const uint4*>(res + col + g * 8);
+        };
+        fetch_resid(part, rr);
 #pragma unroll 1
         for (int c = part; c < BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
+          uint4 rn[4] = {};
+          fetch_resid(c + 2, rn);
           tmem_ld_wait();
           const int col = col0 + c * 32;
-          if (col >= shape.N) continue;
+          if (col < shape.N) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte store
-            const int cg = col + g * 8;
-            if (cg >= shape.N) break;
-            float x[8];
+            for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte store
+              const int cg = col + g * 8;
+              if (cg >= shape.N) break;
+              float x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-            if (epi.bias) {
-              const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
-              const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16(bw[i]);
-                x[2 * i] += f.x;
-                x[2 * i + 1] += f.y;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = bf16_round(x[i]);
-            if (epi.gelu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = bf16_round(gelu_erf(x[i]));
-            }
-            if (epi.scale) {
-              const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
-              const uint32_t sw[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16(sw[i]);
-                x[2 * i] = bf16_round(x[2 * i] * f.x);
-                x[2 * i + 1] = bf16_round(x[2 * i + 1] * f.y);
-              }
-            }
-            if (row_ok) {
-              if (res) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res + cg);
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+              if (epi.bias) {
+                const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
+                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(rw[i]);
+                  const float2 f = unpack_bf16(bw[i]);
                   x[2 * i] += f.x;
                   x[2 * i + 1] += f.y;
                 }
               }
-              uint4 o;
-              o.x = pack_bf16(x[0], x[1]);
-              o.y = pack_bf16(x[2], x[3]);
-              o.z = pack_bf16(x[4], x[5]);
-              o.w = pack_bf16(x[6], x[7]);
-              *reinterpret_cast<uint4*>(out + cg) = o;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = bf16_round(x[i]);
+              if (epi.gelu) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  gelu_erf_x2(x[i], x[i + 1]);
+                  x[i] = bf16_round(x[i]);
+                  x[i + 1] = bf16_round(x[i + 1]);
+                }
+              }
+              if (epi.scale) {
+                const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
+                const uint32_t sw[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(sw[i]);
+                  x[2 * i] = bf16_round(x[2 * i] * f.x);
+                  x[2 * i + 1] = bf16_round(x[2 * i + 1] * f.y);
+                }
+              }
+              if (row_ok) {
+                if (res) {
+                  const uint32_t rw[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16(rw[i]);
+                    x[2 * i] += f.x;
+                    x[2 * i + 1] += f.y;
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16(x[0], x[1]);
+                o.y = pack_bf16(x[2], x[3]);
+                o.z = pack_bf16(x[4], x[5]);
+                o.w = pack_bf16(x[6], x[7]);
+                *reinterpret_cast<uint4*>(out + cg) = o;
+              }
             }
           }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rr[g] = rn[g];
         }
       } else if constexpr (MODE == kModeSwiGLU) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;

@@ -110,7 +110,11 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
           float v = acc[m];
           if (epi.bias) v += __bfloat162float(epi.bias[n]);
           v = bf16_round(v);
-          if (epi.gelu) v = bf16_round(gelu_erf(v));
+          if (epi.gelu) {   // same GELU evaluation as the tensor-core epilogue, so results do not depend on the batch size
+            float unused = 0.f;
+            gelu_erf_x2(v, unused);
+            v = bf16_round(v);
+          }
           if (epi.scale) v = bf16_round(v * __bfloat162float(epi.scale[n]));
           if (epi.resid) v += __bfloat162float(epi.resid[m * epi.ldr + n]);
           reinterpret_cast<__nv_bfloat16*>(epi.out)[m * epi.ldo + n] = __float2bfloat16_rn(v);

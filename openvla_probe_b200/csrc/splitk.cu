@@ -55,7 +55,17 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
     for (int i = 0; i < 8; ++i) {
       if (epi.bias) x[i] += __bfloat162float(epi.bias[j + i]);
       x[i] = bf16_round(x[i]);
-      if (epi.gelu) x[i] = bf16_round(gelu_erf(x[i]));
+    }
+    if (epi.gelu) {   // the same pairwise GELU as the fused GEMM epilogue: split and unsplit results are bit-identical
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        gelu_erf_x2(x[i], x[i + 1]);
+        x[i] = bf16_round(x[i]);
+        x[i + 1] = bf16_round(x[i + 1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
       if (epi.scale) x[i] = bf16_round(x[i] * __bfloat162float(epi.scale[j + i]));
       if (epi.resid) x[i] += __bfloat162float(epi.resid[static_cast<long long>(row) * epi.ldr + j + i]);
     }
