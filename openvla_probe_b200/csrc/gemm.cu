@@ -25,27 +25,33 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D row-major [rows, cols] tensor with `ld` elements between rows; box = [box_rows, 128 bytes]
-int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
-                 int box_rows) {
+// 2-D row-major [rows, cols] tensor with `ld` elements between rows; box = [box_rows, box_bytes] with the swizzle whose
+// span equals the box width (128 or 64 bytes)
+static int make_tmap_2d_box(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                            int box_rows, int box_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15))
     return set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
   return 0;
 }
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows) {
+  return make_tmap_2d_box(m, ptr, elem_bytes, rows, cols, ld, box_rows, 128);
+}
 
 template <int BN, int CG, int MODE, int KIND>
-static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s, const GemmEpi& e,
-                      int num_sms, cudaStream_t stream) {
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                      const GemmShape& s, const GemmEpi& e, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   auto kern = gemm_tcgen05_kernel<BN, CG, MODE, KIND>;
   static bool attr_set = false;
@@ -70,19 +76,19 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSh
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(kCatGemm, 2.0 * s.M * s.N * s.K, 0.0, stream);
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, s, e));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, s, e));
   count_launch();
   return 0;
 }
 
 template <int MODE, int KIND>
-static int dispatch_tile(int bn, int cg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
-                         const GemmEpi& e, int num_sms, cudaStream_t stream) {
-  if (bn == 256 && cg == 2) return launch_one<256, 2, MODE, KIND>(ta, tb, s, e, num_sms, stream);
-  if (bn == 256 && cg == 1) return launch_one<256, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
-  if (bn == 128 && cg == 2) return launch_one<128, 2, MODE, KIND>(ta, tb, s, e, num_sms, stream);
-  if (bn == 128 && cg == 1) return launch_one<128, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
-  if (bn == 64 && cg == 1) return launch_one<64, 1, MODE, KIND>(ta, tb, s, e, num_sms, stream);
+static int dispatch_tile(int bn, int cg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                         const CUtensorMap& tr, const GemmShape& s, const GemmEpi& e, int num_sms, cudaStream_t stream) {
+  if (bn == 256 && cg == 2) return launch_one<256, 2, MODE, KIND>(ta, tb, to, tr, s, e, num_sms, stream);
+  if (bn == 256 && cg == 1) return launch_one<256, 1, MODE, KIND>(ta, tb, to, tr, s, e, num_sms, stream);
+  if (bn == 128 && cg == 2) return launch_one<128, 2, MODE, KIND>(ta, tb, to, tr, s, e, num_sms, stream);
+  if (bn == 128 && cg == 1) return launch_one<128, 1, MODE, KIND>(ta, tb, to, tr, s, e, num_sms, stream);
+  if (bn == 64 && cg == 1) return launch_one<64, 1, MODE, KIND>(ta, tb, to, tr, s, e, num_sms, stream);
   return set_error("gemm: unsupported tile config bn=%d cg=%d", bn, cg);
 }
 
@@ -177,17 +183,31 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     pe.out = splitk_workspace();
     pe.ldo = N;
     pe.ldr = 1LL * M * N;  // slice stride
-    OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, s, pe, num_sms, stream)));
+    OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, ta, ta, s, pe, num_sms, stream)));
     return splitk_epilogue_launch(mode, splitk_workspace(), 1LL * M * N, N, split, M, N, epi, stream);
   }
   GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b};
+  if (kind == kKindBf16 && mode == kModeBf16) {
+    // epilogue through shared memory + TMA (OVLA_GEMM_TMA_EPI=0 keeps the direct per-row stores); needs 16-byte
+    // aligned bases and pitches, otherwise the direct path runs
+    static int g_tma_epi = -1;
+    if (g_tma_epi < 0) { const char* ev = getenv("OVLA_GEMM_TMA_EPI"); g_tma_epi = (ev && ev[0] == '0') ? 0 : 1; }
+    auto aligned = [](const void* ptr, long long ld) { return !(reinterpret_cast<uintptr_t>(ptr) & 15) && !((ld * 2) & 15); };
+    GemmEpi e2 = epi;
+    CUtensorMap to = ta, tr = ta;
+    if (g_tma_epi && aligned(epi.out, epi.ldo) && (!epi.resid || aligned(epi.resid, epi.ldr))) {
+      if (make_tmap_2d_box(&to, epi.out, 2, M, N, epi.ldo, 32, 64)) return -1;
+      if (epi.resid && make_tmap_2d_box(&tr, epi.resid, 2, M, N, epi.ldr, 32, 64)) return -1;
+      e2.tma_epi = 1;
+    }
+    return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, to, tr, s, e2, num_sms, stream);
+  }
   if (kind == kKindBf16) {
-    if (mode == kModeBf16) return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
-    if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
-    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
-    if (mode == kModeQkvRope) return dispatch_tile<kModeQkvRope, kKindBf16>(bn, cg, ta, tb, s, epi, num_sms, stream);
+    if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
+    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
+    if (mode == kModeQkvRope) return dispatch_tile<kModeQkvRope, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
   } else {
-    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindTf32>(bn, cg, ta, tb, s, epi, num_sms, stream);
+    if (mode == kModeF32) return dispatch_tile<kModeF32, kKindTf32>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
   }
   return set_error("gemm: unsupported mode=%d kind=%d", mode, kind);
 }

@@ -45,6 +45,7 @@ struct GemmEpi {
   __nv_bfloat16* k_cache;         // [B, H, Tmax, 128]
   __nv_bfloat16* v_cache;
   int T, pos0, Tmax, H;
+  int tma_epi;  // kModeBf16: output (and residual) tiles move through shared memory with TMA (tensor maps passed beside)
 };
 
 struct GemmShape {
@@ -67,7 +68,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;               // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 32 * 64;         // one [32 rows x 32 bf16] chunk, 64B-swizzled, per epilogue warp
+  static constexpr int kEpiSmemBytes = 2 * kEpiWarps * kEpiStageBytes;  // output + residual staging
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmemBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // Tile rasterisation: groups of G row-tiles sweep all column-tiles, so that a wave of concurrent CTAs touches a
@@ -85,6 +89,7 @@ __device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, in
 template <int BN, int CG, int MODE, int KIND>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmShape shape, const GemmEpi epi) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
@@ -93,11 +98,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // [2][kEpiWarps][2 KB], 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::kEpiSmemBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;                        // [kEpiWarps] residual chunk landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,6 +132,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps * CG);  // one arrive per epilogue warp of every CTA in the group
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -205,6 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int part = (warp - 4) >> 2;   // which half of the column chunks this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;   // parity of this warp's residual-slot barrier
     for (int t = worker; t < num_tiles; t += num_workers) {
       int mb, nb;
       const int slice = t / tiles_mn;
@@ -216,7 +225,107 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const int col0 = nb * BN;
 
-      if constexpr (MODE == kModeBf16) {
+      if (MODE == kModeBf16 && epi.tma_epi) {
+        // Output (and residual) chunks of [32 rows x 32 columns] move through a 64B-swizzled shared-memory slot per
+        // warp with TMA: a thread owns one ROW of the accumulator, so direct global accesses put every lane on its
+        // own 128-byte line (32 L1 wavefronts per instruction, on the same data pipe that feeds the tensor core);
+        // TMA moves whole lines and clips the ragged edges.  In-place residual (out == resid) is safe: a chunk's
+        // residual has landed before the same chunk is stored, and chunks do not overlap.
+        const int ew = warp - 4;
+        uint8_t* so = epi_stage + ew * Cfg::kEpiStageBytes;
+        uint8_t* sr = epi_stage + (kEpiWarps + ew) * Cfg::kEpiStageBytes;
+        const int row0 = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32;
+        const bool has_res = epi.resid != nullptr;
+        const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);       // 64B swizzle: 16-byte piece ^= (row >> 1) & 3
+        auto fetch_res = [&](int c) {
+          if (has_res && lane == 0 && c < BN / 32 && col0 + c * 32 < shape.N) {
+            mbar_expect_tx(&res_bar[ew], Cfg::kEpiStageBytes);
+            tma_load_2d(&tmap_res, &res_bar[ew], sr, col0 + c * 32, row0);
+          }
+        };
+        // (the previous tile's last residual chunk was consumed by every lane before the __syncwarp at its end)
+        fetch_res(part);
+#pragma unroll 1
+        for (int c = part; c < BN / 32; c += 2) {
+          const int col = col0 + c * 32;
+          if (col >= shape.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          uint4 rr[4] = {};
+          if (has_res) {
+            mbar_wait(&res_bar[ew], res_phase);
+            res_phase ^= 1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rr[g] = *reinterpret_cast<const uint4*>(sr + lane * 64 + ((g ^ sw) << 4));
+            __syncwarp();          // every lane has read its row: the slot may be refilled
+            fetch_res(c + 2);
+          }
+          uint4 o4[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cg = col + g * 8;
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+            if (cg < shape.N) {
+              if (epi.bias) {
+                const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
+                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(bw[i]);
+                  x[2 * i] += f.x;
+                  x[2 * i + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = bf16_round(x[i]);
+              if (epi.gelu) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  gelu_erf_x2(x[i], x[i + 1]);
+                  x[i] = bf16_round(x[i]);
+                  x[i + 1] = bf16_round(x[i + 1]);
+                }
+              }
+              if (epi.scale) {
+                const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
+                const uint32_t sw4[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(sw4[i]);
+                  x[2 * i] = bf16_round(x[2 * i] * f.x);
+                  x[2 * i + 1] = bf16_round(x[2 * i + 1] * f.y);
+                }
+              }
+              if (has_res) {
+                const uint32_t rw[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(rw[i]);
+                  x[2 * i] += f.x;
+                  x[2 * i + 1] += f.y;
+                }
+              }
+            }
+            o4[g].x = pack_bf16(x[0], x[1]);
+            o4[g].y = pack_bf16(x[2], x[3]);
+            o4[g].z = pack_bf16(x[4], x[5]);
+            o4[g].w = pack_bf16(x[6], x[7]);
+          }
+          if (lane == 0) tma_store_wait_read<0>();   // the previous store of this warp has finished reading the slot
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(so + lane * 64 + ((g ^ sw) << 4)) = o4[g];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, so, col, row0);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (MODE == kModeBf16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
         const __nv_bfloat16* res = (epi.resid && row_ok) ? epi.resid + static_cast<long long>(row) * epi.ldr : nullptr;
         // The residual row segment of a chunk (64 B per thread, rows a full pitch apart) is fetched one chunk ahead:
@@ -443,6 +552,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   // ------------------------------------------------------------ teardown
+  if (warp >= 4 && lane == 0) tma_store_wait<0>();   // bulk stores read shared memory: finish before the CTA exits
   __syncwarp();
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
