@@ -187,7 +187,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     return splitk_epilogue_launch(mode, splitk_workspace(), 1LL * M * N, N, split, M, N, epi, stream);
   }
   GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b};
-  if (kind == kKindBf16 && mode == kModeBf16) {
+  if (kind == kKindBf16 && (mode == kModeBf16 || mode == kModeSwiGLU)) {
     // epilogue through shared memory + TMA (OVLA_GEMM_TMA_EPI=0 keeps the direct per-row stores); needs 16-byte
     // aligned bases and pitches, otherwise the direct path runs
     static int g_tma_epi = -1;
@@ -196,14 +196,14 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     GemmEpi e2 = epi;
     CUtensorMap to = ta, tr = ta;
     if (g_tma_epi && aligned(epi.out, epi.ldo) && (!epi.resid || aligned(epi.resid, epi.ldr))) {
-      if (make_tmap_2d_box(&to, epi.out, 2, M, N, epi.ldo, 32, 64)) return -1;
+      if (make_tmap_2d_box(&to, epi.out, 2, M, mode == kModeSwiGLU ? N / 2 : N, epi.ldo, 32, 64)) return -1;
       if (epi.resid && make_tmap_2d_box(&tr, epi.resid, 2, M, N, epi.ldr, 32, 64)) return -1;
       e2.tma_epi = 1;
     }
+    if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, to, tr, s, e2, num_sms, stream);
     return dispatch_tile<kModeBf16, kKindBf16>(bn, cg, ta, tb, to, tr, s, e2, num_sms, stream);
   }
   if (kind == kKindBf16) {
-    if (mode == kModeSwiGLU) return dispatch_tile<kModeSwiGLU, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
     if (mode == kModeF32) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
     if (mode == kModeQkvRope) return dispatch_tile<kModeQkvRope, kKindBf16>(bn, cg, ta, tb, ta, ta, s, epi, num_sms, stream);
   } else {

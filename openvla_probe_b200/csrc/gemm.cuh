@@ -56,6 +56,9 @@ struct GemmShape {
   unsigned long long l2_a, l2_b;  // L2 eviction-priority hints of the A / W tile loads (kL2Evict*)
 };
 
+#ifndef OVLA_EPI_SLOTS
+#define OVLA_EPI_SLOTS 1
+#endif
 static constexpr int kGemmThreads = 384;
 static constexpr int kEpiWarps = 8;
 static constexpr int kBM = 128;           // rows per CTA
@@ -66,11 +69,14 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CG;                 // W rows staged per CTA
   static constexpr int kStageBBytes = kBRows * 128;
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  // staging slots per epilogue warp and direction: 2 where the operand ring keeps >= 5 stages, else 1
+  static constexpr int kEpiSlots = (OVLA_EPI_SLOTS >= 2 && kStageBytes <= 32 * 1024) ? 2 : 1;
+  static constexpr int kRing = (232448 - 1024 - 512 - 2 * kEpiSlots * 8 * 2048);   // bytes left for the operand ring
+  static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;               // 256 or 512 (power of two)
   static constexpr int kEpiStageBytes = 32 * 64;         // one [32 rows x 32 bf16] chunk, 64B-swizzled, per epilogue warp
-  static constexpr int kEpiSmemBytes = 2 * kEpiWarps * kEpiStageBytes;  // output + residual staging
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmemBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiSmemBytes = 2 * kEpiSlots * kEpiWarps * kEpiStageBytes;  // output + residual staging
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmemBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -98,13 +104,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // [2][kEpiWarps][2 KB], 1024-byte aligned
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // [out | resid][slot][kEpiWarps][2 KB], 1024-byte aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::kEpiSmemBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;                        // [kEpiWarps] residual chunk landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint64_t* res_bar = tmem_empty + 2;                        // [slot][kEpiWarps] residual chunk landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + Cfg::kEpiSlots * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,7 +138,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps * CG);  // one arrive per epilogue warp of every CTA in the group
     }
-    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
+    for (int w = 0; w < Cfg::kEpiSlots * kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -213,7 +219,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int part = (warp - 4) >> 2;   // which half of the column chunks this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t res_phase = 0;   // parity of this warp's residual-slot barrier
+    uint32_t res_phase = 0;   // bit s: parity of this warp's residual-slot barrier s
+    uint32_t n_out = 0, n_res = 0;   // chunks this warp has stored / residual chunks it has requested and consumed
+    uint32_t n_req = 0;
     for (int t = worker; t < num_tiles; t += num_workers) {
       int mb, nb;
       const int slice = t / tiles_mn;
@@ -231,20 +239,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // own 128-byte line (32 L1 wavefronts per instruction, on the same data pipe that feeds the tensor core);
         // TMA moves whole lines and clips the ragged edges.  In-place residual (out == resid) is safe: a chunk's
         // residual has landed before the same chunk is stored, and chunks do not overlap.
+        constexpr int SL = Cfg::kEpiSlots;
         const int ew = warp - 4;
-        uint8_t* so = epi_stage + ew * Cfg::kEpiStageBytes;
-        uint8_t* sr = epi_stage + (kEpiWarps + ew) * Cfg::kEpiStageBytes;
+        auto out_slot = [&](uint32_t i) { return epi_stage + ((i % SL) * kEpiWarps + ew) * Cfg::kEpiStageBytes; };
+        auto res_slot = [&](uint32_t i) { return epi_stage + ((SL + i % SL) * kEpiWarps + ew) * Cfg::kEpiStageBytes; };
         const int row0 = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32;
         const bool has_res = epi.resid != nullptr;
         const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);       // 64B swizzle: 16-byte piece ^= (row >> 1) & 3
+        // residual chunks are requested SL chunks ahead (slot = request number % SL; a slot is refilled only after
+        // every lane has read it)
         auto fetch_res = [&](int c) {
-          if (has_res && lane == 0 && c < BN / 32 && col0 + c * 32 < shape.N) {
-            mbar_expect_tx(&res_bar[ew], Cfg::kEpiStageBytes);
-            tma_load_2d(&tmap_res, &res_bar[ew], sr, col0 + c * 32, row0);
+          if (has_res && c < BN / 32 && col0 + c * 32 < shape.N) {
+            if (lane == 0) {
+              uint64_t* bar = &res_bar[(n_req % SL) * kEpiWarps + ew];
+              mbar_expect_tx(bar, Cfg::kEpiStageBytes);
+              tma_load_2d(&tmap_res, bar, res_slot(n_req), col0 + c * 32, row0);
+            }
+            ++n_req;
           }
         };
-        // (the previous tile's last residual chunk was consumed by every lane before the __syncwarp at its end)
-        fetch_res(part);
+#pragma unroll
+        for (int i = 0; i < SL; ++i) fetch_res(part + 2 * i);
 #pragma unroll 1
         for (int c = part; c < BN / 32; c += 2) {
           const int col = col0 + c * 32;
@@ -254,12 +269,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           uint4 rr[4] = {};
           if (has_res) {
-            mbar_wait(&res_bar[ew], res_phase);
-            res_phase ^= 1;
+            const uint32_t sl = n_res % SL;
+            mbar_wait(&res_bar[sl * kEpiWarps + ew], (res_phase >> sl) & 1);
+            res_phase ^= 1u << sl;
+            const uint8_t* sr = res_slot(n_res);
 #pragma unroll
             for (int g = 0; g < 4; ++g) rr[g] = *reinterpret_cast<const uint4*>(sr + lane * 64 + ((g ^ sw) << 4));
+            ++n_res;
             __syncwarp();          // every lane has read its row: the slot may be refilled
-            fetch_res(c + 2);
+            fetch_res(c + 2 * SL);
           }
           uint4 o4[4];
 #pragma unroll
@@ -314,7 +332,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             o4[g].z = pack_bf16(x[4], x[5]);
             o4[g].w = pack_bf16(x[6], x[7]);
           }
-          if (lane == 0) tma_store_wait_read<0>();   // the previous store of this warp has finished reading the slot
+          uint8_t* so = out_slot(n_out);
+          if (lane == 0) tma_store_wait_read<SL - 1>();   // the store that last used this slot has finished reading it
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(so + lane * 64 + ((g ^ sw) << 4)) = o4[g];
@@ -324,6 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_2d(&tmap_out, so, col, row0);
             tma_store_commit();
           }
+          ++n_out;
         }
       } else if constexpr (MODE == kModeBf16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
@@ -406,6 +426,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) rr[g] = rn[g];
+        }
+      } else if (MODE == kModeSwiGLU && epi.tma_epi) {
+        // same shared-memory + TMA store as the bf16 mode: a 64-column accumulator chunk ([32 gate | 32 up]) gives one
+        // [32 x 32] output chunk
+        constexpr int SL = Cfg::kEpiSlots;
+        const int ew = warp - 4;
+        const int row0 = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32;
+        const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+        const int n_cols = shape.N / 2;
+#pragma unroll 1
+        for (int c = part; c < BN / 64; c += 2) {
+          const int col = (col0 + c * 64) / 2;
+          if (col >= n_cols) break;
+          uint32_t g[32], u[32];
+          tmem_ld32(taddr + c * 64, g);
+          tmem_ld32(taddr + c * 64 + 32, u);
+          tmem_ld_wait();
+          uint4 o4[4];
+#pragma unroll
+          for (int grp = 0; grp < 4; ++grp) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]));
+              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]));
+              y[i] = bf16_round(silu(gv)) * uv;
+            }
+            o4[grp].x = pack_bf16(y[0], y[1]);
+            o4[grp].y = pack_bf16(y[2], y[3]);
+            o4[grp].z = pack_bf16(y[4], y[5]);
+            o4[grp].w = pack_bf16(y[6], y[7]);
+          }
+          uint8_t* so = epi_stage + ((n_out % SL) * kEpiWarps + ew) * Cfg::kEpiStageBytes;
+          if (lane == 0) tma_store_wait_read<SL - 1>();
+          __syncwarp();
+#pragma unroll
+          for (int grp = 0; grp < 4; ++grp) *reinterpret_cast<uint4*>(so + lane * 64 + ((grp ^ sw) << 4)) = o4[grp];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, so, col, row0);
+            tma_store_commit();
+          }
+          ++n_out;
         }
       } else if constexpr (MODE == kModeSwiGLU) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
