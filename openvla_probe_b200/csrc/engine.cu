@@ -96,6 +96,11 @@ struct OvlaEngine {
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
   bool attn_tc = true;    // OVLA_ATTN_TC=0 falls back to the mma.sync flash kernel for head_dim 64 / 128 (A/B runs)
   bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
+  // ovla_run_host, eager (non-graph) passes: each layer's pooled row block goes to the host on a copy stream as soon
+  // as its pooling kernel is done, under the rest of the pass
+  float* pooled_host_async = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_pool = nullptr, ev_copied = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<GraphKey, GraphEntry> graphs;
@@ -272,6 +277,9 @@ extern "C" void ovla_destroy(OvlaEngine* e) {
   cudaSetDevice(e->device);
   for (auto& kv : e->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->ev_pool) cudaEventDestroy(e->ev_pool);
+  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -507,6 +515,17 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::Vit
 // Llama prefill over all B*T rows: RMSNorm -> QKV GEMM -> RoPE + KV write -> causal flash attention -> o_proj(+res)
 // -> RMSNorm -> gate/up GEMM with SwiGLU epilogue -> down(+res); the capture kernel pools the residual stream
 // (hidden_states[i], i < L) before each layer and the post-final-norm states (hidden_states[L]) at the end.
+// D2H of one layer's pooled block [B, D] behind its pooling kernel (host runs only; see pooled_host_async)
+static int pooled_to_host(OvlaEngine* e, int layer, int B, cudaStream_t st) {
+  if (!e->pooled_host_async) return 0;
+  const long long D = e->d.llm_dim, off = 1LL * layer * B * D;
+  CUDA_TRY(cudaEventRecord(e->ev_pool, st));
+  CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_pool, 0));
+  CUDA_TRY(cudaMemcpyAsync(e->pooled_host_async + off, e->pooled + off, sizeof(float) * B * D, cudaMemcpyDeviceToHost,
+                           e->copy_stream));
+  return 0;
+}
+
 int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t st) {
   const OvlaDims& d = e->d;
   const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim, rows = B * T;
@@ -519,6 +538,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
     if (a->pool_len > 0)
       OVLA_TRY(pool_tokens_launch(e->l_x, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
                                   e->pooled + 1LL * i * B * D, D, st));
+    if (a->pool_len > 0) OVLA_TRY(pooled_to_host(e, i, B, st));
     if (a->hidden_out_dev)
       CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
                                sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
@@ -556,6 +576,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
   if (a->pool_len > 0)
     OVLA_TRY(pool_tokens_launch(e->l_h, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
                                 e->pooled + 1LL * d.llm_layers * B * D, D, st));
+  if (a->pool_len > 0) OVLA_TRY(pooled_to_host(e, d.llm_layers, B, st));
   if (a->hidden_out_dev)
     CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * d.llm_layers * rows * D, e->l_h,
                              sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
@@ -673,10 +694,15 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
 // Small batches are launch-bound (~2000 kernels per pass): the whole pass is captured once per distinct argument set
 // into a CUDA graph on the engine's own stream and replayed afterwards.  The first call with a new key runs eagerly
 // (it also performs the one-time cudaFuncSetAttribute calls), the second captures, later calls replay.
+// passes that may be replayed from a CUDA graph (small batches; never while the per-kernel profiler records events)
+static bool graph_eligible(const OvlaEngine* e, const OvlaRunArgs* a) {
+  return a->B > 0 && a->B <= e->graph_max_batch && !prof_enabled();
+}
+
 extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
   if (!e || !a) return set_error("ovla_run: null argument");
   cudaStream_t user = static_cast<cudaStream_t>(stream);
-  if (a->B <= 0 || a->B > e->graph_max_batch || prof_enabled()) return run_impl(e, a, user);
+  if (!graph_eligible(e, a)) return run_impl(e, a, user);
   CUDA_TRY(cudaSetDevice(e->device));
   GraphKey key;
   memset(&key, 0, sizeof(key));  // field-wise copy keeps the padding bytes zero for the memcmp ordering
@@ -757,10 +783,26 @@ extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const voi
   a.pool_mode = pool_mode;
   a.n_new_tokens = tokens_host ? n_new : 0;
   a.tokens_out_dev = e->out_tokens;
-  OVLA_TRY(ovla_run(e, &a, st));
-  if (a.pool_len > 0)
+  // eager passes (no CUDA graph: B above the graph limit or graphs disabled) stream the pooled states out layer by layer
+  const bool stream_pooled = a.pool_len > 0 && !graph_eligible(e, &a);
+  if (stream_pooled) {
+    if (!e->copy_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_pool, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
+    }
+    e->pooled_host_async = pooled_host;
+  }
+  const int rc_run = ovla_run(e, &a, st);
+  e->pooled_host_async = nullptr;
+  if (rc_run) return rc_run;
+  if (stream_pooled) {
+    CUDA_TRY(cudaEventRecord(e->ev_copied, e->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, e->ev_copied, 0));
+  } else if (a.pool_len > 0) {
     CUDA_TRY(cudaMemcpyAsync(pooled_host, e->pooled, sizeof(float) * (d.llm_layers + 1LL) * B * d.llm_dim,
                              cudaMemcpyDeviceToHost, st));
+  }
   if (a.n_new_tokens > 0)
     CUDA_TRY(cudaMemcpyAsync(tokens_host, e->out_tokens, sizeof(long long) * B * n_new, cudaMemcpyDeviceToHost, st));
   int err = 0;

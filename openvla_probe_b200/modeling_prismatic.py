@@ -201,14 +201,18 @@ class OpenVLAForActionPrediction:
                                    layer_indices: Optional[Sequence[int]] = None, pooling_method: str = "mean",
                                    **kwargs: Any):
         """Fused equivalent of get_vla_action's two passes.  Returns (embeds, actions): embeds maps each requested
-        layer index (negative allowed, default (-1,), openvla_utils.py:193-199) to fp32 [B, D] pooled states."""
+        layer index (negative allowed, default (-1,), openvla_utils.py:193-199) to fp32 [B, D] pooled states.
+
+        ``pooled_out=`` (keyword, optional): a caller-owned CPU float32 tensor [n_layers + 1, B, D] (ideally pinned)
+        that receives the pooled states directly from the device -- the returned arrays are then views of it and no
+        fresh 138 MB result is allocated per call (numpy's ``out=`` convention)."""
         actions, pooled = self._predict(input_ids, unnorm_key, capture=True, pooling_method=pooling_method, **kwargs)
         n = pooled.shape[0]
         embeds = {idx: pooled[idx if idx >= 0 else n + idx] for idx in (layer_indices or (-1,))}
         return embeds, actions
 
     def _predict(self, input_ids, unnorm_key, capture: bool, pooling_method: str = "mean", pixel_values=None,
-                 attention_mask=None, do_sample: bool = False, return_tokens: bool = False, **unused):
+                 attention_mask=None, do_sample: bool = False, return_tokens: bool = False, pooled_out=None, **unused):
         if do_sample:
             raise ValueError("only greedy decoding (do_sample=False) is implemented, as used by the reference path")
         self._check_inputs(input_ids, pixel_values, attention_mask)
@@ -239,10 +243,23 @@ class OpenVLAForActionPrediction:
                 px_p = self._pinned("px", tuple(pixel_values.shape), torch.bfloat16)
                 px_p.copy_(pixel_values)
             tok_p = self._pinned("tok", (B, n_act), torch.int64)
-            pool_p = self._pinned("pool", (tc.num_hidden_layers + 1, B, tc.hidden_size), torch.float32) if capture else None
+            pool_shape = (tc.num_hidden_layers + 1, B, tc.hidden_size)
+            own_out = capture and pooled_out is not None
+            if own_out:
+                if (not isinstance(pooled_out, torch.Tensor) or pooled_out.is_cuda or pooled_out.dtype != torch.float32
+                        or tuple(pooled_out.shape) != pool_shape or not pooled_out.is_contiguous()):
+                    raise ValueError(f"pooled_out must be a contiguous CPU float32 tensor of shape {pool_shape}")
+                pool_p = pooled_out
+            else:
+                pool_p = self._pinned("pool", pool_shape, torch.float32) if capture else None
             self.engine.run_host(ids_p, px_p, pool_len, pool_mode, n_act, pool_p, tok_p)
             tokens = tok_p.numpy().copy()
-            pooled = pool_p.numpy().copy() if capture else None
+            if not capture:
+                pooled = None
+            elif own_out:
+                pooled = pool_p.numpy()               # the caller's buffer: views, no copy
+            else:
+                pooled = torch.empty(pool_shape, dtype=torch.float32).copy_(pool_p).numpy()   # threaded copy out of staging
         final_ids = self._finish_sequences(ids, tokens, n_act)
         actions = self._detokenize(final_ids, unnorm_key)
         if B == 1:

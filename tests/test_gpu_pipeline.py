@@ -118,6 +118,28 @@ def test_host_and_device_entry_points_agree():
     assert np.array_equal(a_host, a_dev) and np.array_equal(p_host, p_dev)
 
 
+def test_host_path_streams_pooled_states_and_fills_caller_buffer():
+    """B above the CUDA-graph limit (16) takes the eager pass, where ovla_run_host copies each layer's pooled block to
+    the host behind its pooling kernel; with `pooled_out=` the block lands in the caller's (pinned) buffer and the
+    returned arrays are views of it.  Repeated calls and the device entry point give identical bits."""
+    od, pc, W, model, ids, px = _build(B=20, P=8)
+    tc = pc.text_config
+    a_dev, p_dev = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda())
+    out = torch.full((tc.num_hidden_layers + 1, 20, tc.hidden_size), float("nan"), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        out.fill_(float("nan"))
+        a_host, p_host = model._predict(ids, "synthetic", capture=True, pixel_values=px, pooled_out=out)
+        assert p_host.ctypes.data == out.data_ptr()                       # views of the caller's buffer
+        assert np.array_equal(a_host, a_dev) and np.array_equal(p_host, p_dev)
+    a2, p2 = model._predict(ids, "synthetic", capture=True, pixel_values=px)      # fresh-result path
+    assert np.array_equal(p2, p_dev) and p2.ctypes.data != out.data_ptr()
+    embeds, _ = model.predict_action_and_capture(ids, unnorm_key="synthetic", layer_indices=[0, -1], pixel_values=px,
+                                                 pooled_out=out)
+    assert np.array_equal(embeds[-1], p_dev[-1]) and np.array_equal(embeds[0], p_dev[0])
+    with pytest.raises(ValueError):
+        model._predict(ids, "synthetic", capture=True, pixel_values=px, pooled_out=torch.zeros(3, 3))
+
+
 def test_error_behaviour():
     from openvla_probe_b200 import _lib
 
