@@ -11,6 +11,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base dem
     --log-file gpurun_out/${R}_launches.csv $CMD > gpurun_out/${R}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 210 -c 4 \
     -o gpurun_out/${R}_gemm -f $CMD > gpurun_out/${R}_ncu_gemm.log 2>&1
+if [ -n "$NCU_LIGHT" ]; then
+  ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 26 -c 2 \
+      -o gpurun_out/${R}_attn_tc -f $CMD > gpurun_out/${R}_ncu_attn_tc.log 2>&1
+  ls -la gpurun_out/ | grep ${R}_ | tail -20
+  exit 0
+fi
 ncu --set full --clock-control none --import-source on -k regex:decode_rope_attn -s 4 -c 2 \
     -o gpurun_out/${R}_decode_attn -f $CMD > gpurun_out/${R}_ncu_decode.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:flash_attn -s 10 -c 1 \
