@@ -31,6 +31,8 @@ namespace ovla {
 
 int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows);  // gemm.cu
+int make_tmap_3d_slots(CUtensorMap* m, const void* ptr, long long rows, int n_slots, int slot_cols, long long ld,
+                       int box_rows, int box_cols);  // gemm.cu
 
 static constexpr int kTcThreads = 192;       // warps 0..3 softmax / epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
 static constexpr int kTcBC = 64;             // keys per chunk
@@ -69,6 +71,28 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+// 32-byte-swizzled slab (rows of 16 bf16): the 16-column tail of a head_dim that is not a multiple of 64 (72 -> 64 + 8,
+// zero-padded to 16 by the TMA box).  As a K-major operand it is one K = 16 step, as an MN-major one it is N = 16;
+// 8-row groups are 256 bytes apart either way.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
 struct AttnTcParams {
   __nv_bfloat16* out;
   long long ldo;
@@ -81,16 +105,20 @@ struct AttnTcParams {
 
 template <int HD>
 struct AttnTcCfg {
-  static constexpr int kNS = HD / 64;                       // 64-column slabs per operand
+  static constexpr int kNS = HD / 64;                       // 64-column (128-byte swizzled) slabs per operand
+  static constexpr bool kExt = (HD % 64) != 0;              // + one 16-column (32-byte swizzled) slab: head_dim 72
+  static_assert(!kExt || HD % 64 <= 16, "tail slab holds at most 16 columns");
+  static constexpr int kHDP = kNS * 64 + (kExt ? 16 : 0);   // head_dim as the tensor core sees it
   static constexpr int kNK = HD == 128 ? 3 : 4;             // K ring depth
   static constexpr int kNV = HD == 128 ? 2 : 4;             // V ring depth
-  static constexpr int kQBytes = kNS * kSlabQ;
-  static constexpr int kChunkBytes = kNS * kSlabKV;         // one K (or V) chunk
+  static constexpr int kQBytes = kNS * kSlabQ + (kExt ? 128 * 32 : 0);
+  static constexpr int kChunkBytes = kNS * kSlabKV + (kExt ? kTcBC * 32 : 0);   // one K (or V) chunk
   static constexpr int kKOff = kQBytes;
   static constexpr int kVOff = kKOff + kNK * kChunkBytes;
   static constexpr int kBarOff = kVOff + kNV * kChunkBytes;
   static constexpr int kSmemBytes = kBarOff + 256;          // + barriers; the base must be 1024-byte aligned (checked)
-  static constexpr int kTmemCols = 256;                     // S/P ping-pong [0,128) | O [128, 128+HD)
+  static constexpr int kTmemCols = 256;                     // S/P ping-pong [0,128) | O [128, 128+kHDP)
+  static_assert(kQBytes % 1024 == 0 && kChunkBytes % 1024 == 0, "slabs stay 1024-byte aligned");
   static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 };
 
@@ -107,10 +135,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-               const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_qx,
+               const __grid_constant__ CUtensorMap tmap_kvx, const AttnTcParams p) {
   using Cfg = AttnTcCfg<HD>;
   constexpr int NS = Cfg::kNS;
   constexpr int NK = Cfg::kNK, NV = Cfg::kNV;
+  constexpr bool EXT = Cfg::kExt;      // head_dim 72: operands are [64-column slab | 16-column slab], loaded through
+  constexpr int HDP = Cfg::kHDP;       // 3-D tensor maps (column in head, head slot, row) so that the tail zero-fills
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023)) {
     printf("attn_tc_kernel: dynamic shared memory base is not 1024-byte aligned\n");
@@ -199,26 +230,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const Item it = item_of(w);
         if (k > 0) mbar_wait(bar_qfree, (k - 1) & 1);   // every QK^T product of the previous item has read Q
         mbar_expect_tx(bar_q, Cfg::kQBytes);
+        if constexpr (EXT) {
+          tma_load_3d(&tmap_q, bar_q, sQ, 0, it.h, it.b * p.T + it.q0);
+          tma_load_3d(&tmap_qx, bar_q, sQ + NS * kSlabQ, 64, it.h, it.b * p.T + it.q0);
+        } else {
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl)
-          tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, it.h * p.q_col_per_h + sl * 64, it.b * p.T + it.q0);
+          for (int sl = 0; sl < NS; ++sl)
+            tma_load_2d(&tmap_q, bar_q, sQ + sl * kSlabQ, it.h * p.q_col_per_h + sl * 64, it.b * p.T + it.q0);
+        }
         const int kv_row = it.b * p.kv_rows_per_b + it.h * p.kv_rows_per_h;
         const int k_col = p.k_col0 + it.h * p.kv_col_per_h, v_col = p.v_col0 + it.h * p.kv_col_per_h;
         auto load_k = [&](int c) {
           const uint32_t cur = cur0 + c, s = cur % NK;
           if (cur >= NK) mbar_wait(bar_kfree + s, (cur / NK - 1) & 1);
           mbar_expect_tx(bar_kfull + s, Cfg::kChunkBytes);
+          if constexpr (EXT) {   // packed qkv: head slots [0,H) q, [H,2H) k, [2H,3H) v
+            tma_load_3d(&tmap_k, bar_kfull + s, sK(s), 0, p.H + it.h, kv_row + c * kTcBC);
+            tma_load_3d(&tmap_kvx, bar_kfull + s, sK(s) + NS * kSlabKV, 64, p.H + it.h, kv_row + c * kTcBC);
+          } else {
 #pragma unroll
-          for (int sl = 0; sl < NS; ++sl)
-            tma_load_2d(&tmap_k, bar_kfull + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+            for (int sl = 0; sl < NS; ++sl)
+              tma_load_2d(&tmap_k, bar_kfull + s, sK(s) + sl * kSlabKV, k_col + sl * 64, kv_row + c * kTcBC);
+          }
         };
         auto load_v = [&](int c) {
           const uint32_t cur = cur0 + c, s = cur % NV;
           if (cur >= NV) mbar_wait(bar_vfree + s, (cur / NV - 1) & 1);
           mbar_expect_tx(bar_vfull + s, Cfg::kChunkBytes);
+          if constexpr (EXT) {
+            tma_load_3d(&tmap_v, bar_vfull + s, sV(s), 0, 2 * p.H + it.h, kv_row + c * kTcBC);
+            tma_load_3d(&tmap_kvx, bar_vfull + s, sV(s) + NS * kSlabKV, 64, 2 * p.H + it.h, kv_row + c * kTcBC);
+          } else {
 #pragma unroll
-          for (int sl = 0; sl < NS; ++sl)
-            tma_load_2d(&tmap_v, bar_vfull + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+            for (int sl = 0; sl < NS; ++sl)
+              tma_load_2d(&tmap_v, bar_vfull + s, sV(s) + sl * kSlabKV, v_col + sl * 64, kv_row + c * kTcBC);
+          }
         };
         // K runs one chunk ahead of V: the order of the waits then matches the order in which the products retire
         load_k(0);
@@ -233,7 +279,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // ------------------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(1, 128, 0);                    // N filled in per chunk
-      constexpr uint32_t idesc_o = umma_idesc(1, 128, HD) | (1u << 16);      // B (= V) is MN-major
+      constexpr uint32_t idesc_o = umma_idesc(1, 128, NS * 64) | (1u << 16);   // B (= V) is MN-major
+      constexpr uint32_t idesc_ox = umma_idesc(1, 128, 16) | (1u << 16);       // the 16-column tail of V
       uint32_t cur0 = 0;
       for (int k = 0;; ++k) {
         const uint32_t w = work(k);
@@ -249,11 +296,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             tc_fence_after();
             const uint32_t idesc = idesc_s | (static_cast<uint32_t>(nc >> 3) << 17);
 #pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks) {
+            for (int ks = 0; ks < NS * 4; ++ks) {
               const uint64_t a = umma_desc_sw128(smem_u32(sQ + (ks >> 2) * kSlabQ)) + 2 * (ks & 3);
               const uint64_t bd = umma_desc_sw128(smem_u32(sK(cur % NK) + (ks >> 2) * kSlabKV)) + 2 * (ks & 3);
               umma_bf16<1>(tmem + s * kTcBC, a, bd, idesc, ks != 0);
             }
+            if constexpr (EXT)   // columns 64..79 of the head (72..79 are zeros)
+              umma_bf16<1>(tmem + s * kTcBC, umma_desc_sw32(smem_u32(sQ + NS * kSlabQ)),
+                           umma_desc_sw32(smem_u32(sK(cur % NK) + NS * kSlabKV)), idesc, 1u);
             umma_commit(bar_kfree + cur % NK);
             umma_commit(bar_s + s);
             if (c == it.n_chunks - 1) umma_commit(bar_qfree);
@@ -270,6 +320,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int j = 0; j < nc / 16; ++j) {
               const uint64_t bd = umma_desc_mn_sw128(smem_u32(sV(cur % NV) + j * 16 * 128), kSlabKV);
               umma_bf16_ts(tmem + 128, tmem + s * kTcBC + 8 * j, bd, idesc_o, (cp > 0 || j > 0) ? 1u : 0u);
+              if constexpr (EXT)
+                umma_bf16_ts(tmem + 128 + NS * 64, tmem + s * kTcBC + 8 * j,
+                             umma_desc_sw32(smem_u32(sV(cur % NV) + NS * kSlabKV + j * 16 * 32)), idesc_ox,
+                             (cp > 0 || j > 0) ? 1u : 0u);
             }
             umma_commit(bar_vfree + cur % NV);
             if (cp == it.n_chunks - 1) umma_commit(bar_done);
@@ -340,13 +394,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           mbar_wait(bar_vfree + (cur - 1) % NV, ((cur - 1) / NV) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < HD / 32; ++cc) {
+          for (int cc = 0; cc < HDP / 32; ++cc) {
             uint32_t o[32];
             tmem_ld32(lane_base + 128 + cc * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
             tmem_st32(lane_base + 128 + cc * 32, o);
+          }
+          if constexpr (HDP % 32 != 0) {
+            uint32_t o[16];
+            tmem_ld16(lane_base + 128 + (HDP / 32) * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st16(lane_base + 128 + (HDP / 32) * 32, o);
           }
           tmem_st_wait();
         }
@@ -374,11 +436,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.T + t_row) * p.ldo + it.h * HD;
 #pragma unroll 1
-      for (int cc = 0; cc < HD / 32; ++cc) {
+      for (int cc = 0; cc < HDP / 32; ++cc) {
         uint32_t o[32];
         tmem_ld32(lane_base + 128 + cc * 32, o);
         tmem_ld_wait();
-        if (cc == HD / 32 - 1) {   // O is in registers: the next item's first PV product may overwrite it
+        if (HDP % 32 == 0 && cc == HDP / 32 - 1) {   // O is in registers: the next item's first PV product may overwrite it
           tc_fence_before();
           mbar_arrive(bar_ofree);
         }
@@ -394,6 +456,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
         }
       }
+      if constexpr (HDP % 32 != 0) {   // tail: 16 accumulator columns, of which HD - 64*NS (= 8) are real
+        uint32_t o[16];
+        tmem_ld16(lane_base + 128 + (HDP / 32) * 32, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_ofree);
+        if (t_row >= 0) {
+          static_assert(HDP % 32 == 0 || HD - (HDP / 32) * 32 == 8, "tail store writes exactly 8 columns");
+          uint4 o4;
+          o4.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          o4.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          o4.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          o4.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          *reinterpret_cast<uint4*>(dst + (HDP / 32) * 32) = o4;
+        }
+      }
     }
     tc_fence_before();
   }
@@ -405,8 +483,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 }
 
 template <int HD, bool CAUSAL>
-static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
-                              int B, cudaStream_t st) {
+static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tqx,
+                              const CUtensorMap& tkvx, const AttnTcParams& p, int B, cudaStream_t st) {
   using Cfg = AttnTcCfg<HD>;
   auto kern = attn_tc_kernel<HD, CAUSAL>;
   static bool attr = false;
@@ -427,7 +505,7 @@ static int attn_tc_launch_one(const CUtensorMap& tq, const CUtensorMap& tk, cons
   while (n_tiles > 1 && gcd((static_cast<int>(grid.x) + pp.rot) % n_tiles, n_tiles) != 1) ++pp.rot;
   const double pairs = CAUSAL ? 0.5 * p.T * (p.T + 1.0) : 1.0 * p.T * p.T;
   ProfScope prof(kCatFlash, 4.0 * B * p.H * pairs * HD, 2.0 * B * p.H * HD * (4.0 * p.T), st);
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, pp);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, tqx, tkvx, pp);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
@@ -451,18 +529,16 @@ int attn_tc_prefill_launch(const void* q, long long ld_q, const void* kc, const 
   p.kv_rows_per_b = H * Tmax;
   p.kv_rows_per_h = Tmax;
   p.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
-  return attn_tc_launch_one<128, true>(tq, tk, tv, p, B, st);
+  return attn_tc_launch_one<128, true>(tq, tk, tv, tq, tk, p, B, st);
 }
 
-// q, k, v packed as [B*T, 3*H*hd] (q | k | v, head h at columns h*hd of each third); head_dim 64 or 128.
+// q, k, v packed as [B*T, 3*H*hd] (q | k | v, head h at columns h*hd of each third); head_dim 64, 72 (non-causal) or 128.
 int attn_tc_qkv_launch(const void* qkv, long long ld, void* out, long long ldo, int B, int H, int T, int hd, int causal,
                        cudaStream_t st) {
   if (B <= 0 || T <= 0) return 0;
-  if (hd != 64 && hd != 128) return set_error("tcgen05 attention: head_dim %d not supported (64 or 128)", hd);
+  if (hd != 64 && hd != 128 && !(hd == 72 && !causal))
+    return set_error("tcgen05 attention: head_dim %d (causal %d) not supported (64, 128, or 72 non-causal)", hd, causal);
   const long long D = 1LL * H * hd;
-  CUtensorMap tq, tkv;
-  if (make_tmap_2d(&tq, qkv, 2, 1LL * B * T, 3 * D, ld, 128)) return -1;
-  if (make_tmap_2d(&tkv, qkv, 2, 1LL * B * T, 3 * D, ld, kTcBC)) return -1;
   AttnTcParams p = {};
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
@@ -475,10 +551,22 @@ int attn_tc_qkv_launch(const void* qkv, long long ld, void* out, long long ldo, 
   p.v_col0 = static_cast<int>(2 * D);
   p.kv_col_per_h = hd;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
-  if (hd == 64) return causal ? attn_tc_launch_one<64, true>(tq, tkv, tkv, p, B, st)
-                              : attn_tc_launch_one<64, false>(tq, tkv, tkv, p, B, st);
-  return causal ? attn_tc_launch_one<128, true>(tq, tkv, tkv, p, B, st)
-                : attn_tc_launch_one<128, false>(tq, tkv, tkv, p, B, st);
+  if (hd == 72) {
+    if ((ldo * 2) & 15) return set_error("tcgen05 attention: output pitch must be a multiple of 8 elements");
+    CUtensorMap tq, tkv, tqx, tkvx;
+    if (make_tmap_3d_slots(&tq, qkv, 1LL * B * T, 3 * H, hd, ld, 128, 64)) return -1;
+    if (make_tmap_3d_slots(&tkv, qkv, 1LL * B * T, 3 * H, hd, ld, kTcBC, 64)) return -1;
+    if (make_tmap_3d_slots(&tqx, qkv, 1LL * B * T, 3 * H, hd, ld, 128, 16)) return -1;
+    if (make_tmap_3d_slots(&tkvx, qkv, 1LL * B * T, 3 * H, hd, ld, kTcBC, 16)) return -1;
+    return attn_tc_launch_one<72, false>(tq, tkv, tkv, tqx, tkvx, p, B, st);
+  }
+  CUtensorMap tq, tkv;
+  if (make_tmap_2d(&tq, qkv, 2, 1LL * B * T, 3 * D, ld, 128)) return -1;
+  if (make_tmap_2d(&tkv, qkv, 2, 1LL * B * T, 3 * D, ld, kTcBC)) return -1;
+  if (hd == 64) return causal ? attn_tc_launch_one<64, true>(tq, tkv, tkv, tq, tkv, p, B, st)
+                              : attn_tc_launch_one<64, false>(tq, tkv, tkv, tq, tkv, p, B, st);
+  return causal ? attn_tc_launch_one<128, true>(tq, tkv, tkv, tq, tkv, p, B, st)
+                : attn_tc_launch_one<128, false>(tq, tkv, tkv, tq, tkv, p, B, st);
 }
 
 }  // namespace ovla

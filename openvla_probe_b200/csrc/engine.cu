@@ -494,7 +494,7 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::Vit
     BlockW& b = tw.blocks[i];
     OVLA_TRY(layernorm_launch(v.x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, v.h, D, rows, D, st));
     OVLA_TRY(linear(v.h, D, b.qkv_w, rows, kModeBf16, v.qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
-    if (e->attn_tc && hd == 64)
+    if (e->attn_tc && (hd == 64 || hd == 72))
       OVLA_TRY(attn_tc_qkv_launch(v.qkv, 3LL * D, v.attn, D, B, w.heads, N, hd, 0, st));
     else
       OVLA_TRY(flash_attn_launch(v.qkv, v.qkv + D, v.qkv + 2 * D, v.attn, s12, B, w.heads, N, N, hd, 0, st));

@@ -49,6 +49,28 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows
   return make_tmap_2d_box(m, ptr, elem_bytes, rows, cols, ld, box_rows, 128);
 }
 
+// bf16 [rows, n_slots * slot_cols] (pitch `ld` elements) viewed as 3-D (column in slot, slot, row); box =
+// [box_rows, 1 slot, box_cols] with the swizzle whose span equals the box width (128 or 32 bytes).  Columns of a box
+// that lie beyond slot_cols read as zeros: this is how a head of 72 columns is padded to 64 + 16.
+int make_tmap_3d_slots(CUtensorMap* m, const void* ptr, long long rows, int n_slots, int slot_cols, long long ld,
+                       int box_rows, int box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15) || ((slot_cols * 2) & 15))
+    return set_error("TMA operand must be 16-byte aligned with 16-byte multiple pitches");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(slot_cols), static_cast<cuuint64_t>(n_slots), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(slot_cols) * 2, static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 1, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int box_bytes = box_cols * 2;
+  if (box_bytes != 128 && box_bytes != 32) return set_error("make_tmap_3d_slots: box of %d bytes", box_bytes);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (3-D) failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
 template <int BN, int CG, int MODE, int KIND>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                       const GemmShape& s, const GemmEpi& e, int num_sms, cudaStream_t stream) {

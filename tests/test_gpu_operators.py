@@ -198,9 +198,12 @@ def test_prefill_attention_tcgen05_vs_oracle(L, B, H, T, Tmax, qscale):
 
 @pytest.mark.parametrize("B,H,T,hd,causal,qscale", [(2, 2, 21, 64, 0, 1.0), (1, 16, 261, 64, 0, 1.0), (3, 4, 256, 64, 0, 1.0),
                                                     (2, 3, 261, 64, 0, 5.0), (2, 2, 130, 64, 1, 1.0),
-                                                    (2, 2, 200, 128, 0, 1.0), (1, 2, 283, 128, 1, 4.0)])
+                                                    (2, 2, 200, 128, 0, 1.0), (1, 2, 283, 128, 1, 4.0),
+                                                    (2, 16, 256, 72, 0, 1.0), (1, 3, 16, 72, 0, 1.0), (2, 2, 261, 72, 0, 5.0),
+                                                    (3, 5, 70, 72, 0, 1.0)])
 def test_attention_tcgen05_packed_qkv_vs_oracle(L, B, H, T, hd, causal, qscale):
-    """Same kernel on a packed [B*T, 3D] qkv buffer (the ViT towers' layout), head_dim 64 / 128."""
+    """Same kernel on a packed [B*T, 3D] qkv buffer (the ViT towers' layout), head_dim 64 / 128, and 72 (SigLIP): there
+    each operand is a 64-column slab plus a 16-column slab whose last 8 columns the TMA box zero-fills."""
     _lib, lib = L
     g = torch.Generator().manual_seed(T * hd + causal)
     D = H * hd
