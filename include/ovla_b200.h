@@ -106,6 +106,12 @@ int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long
  * mean/std: fp32 [n_towers*3] on the device.  Bit-identical to torchvision's to_tensor + normalize on the host. */
 int ovla_preprocess_frames(const void* frames_u8_dev, int B, int S, int n_towers, const float* mean_dev,
                            const float* std_dev, void* pixel_values_out_dev, void* stream);
+/* get_vla_action(center_crop=True) (experiments/robot/openvla_utils.py:155-175, crop_and_resize :81-124): centred
+ * square crop of area crop_scale (side sqrt(crop_scale)), bilinear tf.image.crop_and_resize back to out_size x out_size,
+ * uint8 HWC [B,H,W,3] -> uint8 HWC [B,out_size,out_size,3] (float32 [0,1] in between, uint8 by scale 255.5 + truncate
+ * as tf.image.convert_image_dtype(saturate=True)). */
+int ovla_center_crop_frames(const void* frames_u8_dev, int B, int H, int W, float crop_scale, void* out_u8_dev,
+                            int out_size, void* stream);
 /* small-batch (M <= 8) weight-streaming GEMM with the same epilogues as ovla_gemm */
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, void* stream);
@@ -194,6 +200,12 @@ int ovla_probe_bce_grad(const float* z_dev, long long ldz, const signed char* yp
 int ovla_probe_ce3_grad(const float* z_dev, long long ldz, const signed char* yp_dev, long long ldy, int n, int K,
                         int rows_pad, const float* class_w3_host, float* dzt_dev, long long ldt, float* stats_dev,
                         void* stream);
+/* Validation confusion counts on the device (the reference gathers to the host and calls sklearn:
+ * train_object_probes.py:190-206, train_dual_head_final.py:196-232, train_3class_direct.py:196-207).  kind 0 object
+ * (mask y != -1), 1 spatial, 2 dual head (presence counts[0..3], truth counts[4..7]), 3 three-class (counts[3*t+p]).
+ * Binary layout: tp, fp, fn, tn.  y: int8 [n, *] with `keep_dev` (int32 [K], may be NULL) selecting its columns.   */
+int ovla_probe_confusion(const float* z_dev, long long ldz, const signed char* y_dev, long long ldy, const int* keep_dev,
+                         int n, int K, int Kpad, int kind, float thresh, unsigned long long* counts9_dev, void* stream);
 /* out[r] = sum_c a[r, c]  (bias gradient from dzt) */
 int ovla_probe_rowsum(const float* a_dev, long long lda, int rows, int cols, float* out_dev, void* stream);
 /* torch.optim.AdamW step on the flat [W (rows x D) | b (rows)] buffer; gradient rows of head h are divided by

@@ -112,6 +112,16 @@ int ovla_attention_tc_qkv(const void* qkv, long long ld, void* out, long long ld
                           int causal, void* stream) {
   return attn_tc_qkv_launch(qkv, ld, out, ldo, B, H, T, head_dim, causal, static_cast<cudaStream_t>(stream));
 }
+int ovla_center_crop_frames(const void* src_u8, int B, int H, int W, float crop_scale, void* dst_u8, int out_size,
+                            void* stream) {
+  if (!src_u8 || !dst_u8) return set_error("ovla_center_crop_frames: null buffer");
+  return center_crop_launch(src_u8, B, H, W, crop_scale, dst_u8, out_size, static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_confusion(const float* z, long long ldz, const signed char* y, long long ldy, const int* keep, int n, int K,
+                         int Kpad, int kind, float thresh, unsigned long long* counts9, void* stream) {
+  if (!z || !y || !counts9) return set_error("ovla_probe_confusion: null buffer");
+  return probe_confusion_launch(z, ldz, y, ldy, keep, n, K, Kpad, kind, thresh, counts9, static_cast<cudaStream_t>(stream));
+}
 int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
                                void* kc, void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
                                void* stream) {

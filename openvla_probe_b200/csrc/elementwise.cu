@@ -419,4 +419,62 @@ int preprocess_frames_launch(const void* frames_u8, int B, int S, int n_towers, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ center crop
+// The reference's `center_crop=True` branch (experiments/robot/openvla_utils.py:155-175 + crop_and_resize :81-124):
+// uint8 -> float32 / 255 -> tf.image.crop_and_resize(box = centred square of side sqrt(crop_scale), bilinear, to
+// out x out) -> clip [0,1] -> uint8 by tf.image.convert_image_dtype(saturate=True) (scale 255.5, truncate).
+// Arithmetic follows TensorFlow's CPU kernel (crop_and_resize_op.cc): in_y = y1 (H-1) + y * ((y2-y1) (H-1) / (out-1)),
+// lerp across x first, then y, every step a separate fp32 operation (no FMA contraction).
+__global__ void center_crop_kernel(const unsigned char* __restrict__ src, int H, int W, float y1, float x1,
+                                   float hs, float ws, unsigned char* __restrict__ dst, int S, long long n_pix) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
+  if (idx >= n_pix) return;
+  const int x = static_cast<int>(idx % S), y = static_cast<int>((idx / S) % S);
+  const long long b = idx / (static_cast<long long>(S) * S);
+  const float in_y = __fadd_rn(__fmul_rn(y1, static_cast<float>(H - 1)), __fmul_rn(static_cast<float>(y), hs));
+  const float in_x = __fadd_rn(__fmul_rn(x1, static_cast<float>(W - 1)), __fmul_rn(static_cast<float>(x), ws));
+  unsigned char* o = dst + idx * 3;
+  if (in_y < 0.f || in_y > static_cast<float>(H - 1) || in_x < 0.f || in_x > static_cast<float>(W - 1)) {
+    o[0] = o[1] = o[2] = 0;   // extrapolation_value = 0
+    return;
+  }
+  const int ty = static_cast<int>(floorf(in_y)), by = static_cast<int>(ceilf(in_y));
+  const int lx = static_cast<int>(floorf(in_x)), rx = static_cast<int>(ceilf(in_x));
+  const float yl = __fsub_rn(in_y, static_cast<float>(ty)), xl = __fsub_rn(in_x, static_cast<float>(lx));
+  const unsigned char* img = src + b * H * W * 3;
+  const float k = 1.0f / 255.0f;   // convert_image_dtype(uint8 -> float32): multiply by float32(1/255)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = __fmul_rn(static_cast<float>(img[(static_cast<long long>(ty) * W + lx) * 3 + c]), k);
+    const float tr = __fmul_rn(static_cast<float>(img[(static_cast<long long>(ty) * W + rx) * 3 + c]), k);
+    const float bl = __fmul_rn(static_cast<float>(img[(static_cast<long long>(by) * W + lx) * 3 + c]), k);
+    const float br = __fmul_rn(static_cast<float>(img[(static_cast<long long>(by) * W + rx) * 3 + c]), k);
+    const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), xl));
+    const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), xl));
+    float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    const float sc = __fmul_rn(v, 255.5f);
+    o[c] = static_cast<unsigned char>(fminf(fmaxf(sc, 0.f), 255.f));   // saturate, truncate toward zero
+  }
+}
+
+int center_crop_launch(const void* src_u8, int B, int H, int W, float crop_scale, void* dst_u8, int S, cudaStream_t st) {
+  const long long n_pix = static_cast<long long>(B) * S * S;
+  if (n_pix <= 0) return 0;
+  if (H < 2 || W < 2 || S < 2) return set_error("center crop: image and output sides must be >= 2");
+  if (!(crop_scale > 0.f)) return set_error("center crop: crop_scale must be positive");
+  // box as the reference builds it (float32): side = clip(sqrt(scale), 0, 1), offset = (1 - side) / 2
+  const float side = fminf(fmaxf(sqrtf(crop_scale), 0.f), 1.f);
+  const float off = (1.f - side) / 2.f;
+  const float y2 = off + side;
+  const float hs = (y2 - off) * static_cast<float>(H - 1) / static_cast<float>(S - 1);
+  const float ws = (y2 - off) * static_cast<float>(W - 1) / static_cast<float>(S - 1);
+  ProfScope prof(kCatOther, 0.0, n_pix * 3.0 * 5.0, st);
+  center_crop_kernel<<<static_cast<unsigned>((n_pix + 255) / 256), 256, 0, st>>>(
+      static_cast<const unsigned char*>(src_u8), H, W, off, off, hs, ws, static_cast<unsigned char*>(dst_u8), S, n_pix);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace ovla

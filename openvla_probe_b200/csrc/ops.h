@@ -36,6 +36,8 @@ int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void*
 int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
                       int Tq, int Tk, int head_dim, int causal, cudaStream_t st);
 
+int center_crop_launch(const void* src_u8, int B, int H, int W, float crop_scale, void* dst_u8, int S, cudaStream_t st);
+
 // attention_tc.cu: causal prefill attention on tcgen05 (head_dim 128)
 int attn_tc_prefill_launch(const void* q, long long ld_q, const void* kc, const void* vc, void* out, long long ldo, int B,
                            int H, int T, int Tmax, cudaStream_t st);
@@ -80,5 +82,7 @@ int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n
 int probe_ce3_grad_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, int n, int K,
                           int rows_pad, const float* class_w3_host, float* dZT, long long ldt, float* stats,
                           cudaStream_t st);
+int probe_confusion_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, const int* keep, int n,
+                           int K, int Kpad, int kind, float thresh, unsigned long long* counts, cudaStream_t st);
 
 }  // namespace ovla

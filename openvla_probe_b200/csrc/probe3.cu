@@ -3,6 +3,8 @@
 //   loss = sum_i w[t_i] * (-log softmax(z_i)[t_i]) / sum_i w[t_i]         (torch weighted-mean reduction)
 //   dz_ic = w[t_i] * (softmax(z_i)_c - [c == t_i])                        (un-normalised; divide by sum_i w[t_i])
 // Gradient rows are written transposed (dZT [3K padded, n]) for the dW GEMM, like the BCE kernels in probe.cu.
+#include <algorithm>
+
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -82,6 +84,70 @@ int probe_ce3_grad_launch(const float* Z, long long ldz, const signed char* Y, l
   ProfScope prof(kCatOther, 0.0, 25.0 * n * K, st);
   ce3_grad_kernel<<<grid, 256, 0, st>>>(Z, ldz, Y, ldy, n, K, rows_pad, class_w3_host[0], class_w3_host[1],
                                         class_w3_host[2], dZT, ldt, stats);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ validation counters
+// On-device confusion counts for the probe validation metrics (train_object_probes.py:190-206, train_spatial_probes.py,
+// train_dual_head_final.py:196-232, train_3class_direct.py:196-207): the reference gathers logits and labels to the host
+// and calls sklearn; accuracy and F1 only need these integer counts, which are exact and order-independent.
+//   kind 0 (object)  mask y != -1, target y == 1, pred sigmoid(z) > thresh        counts[0..3]  = tp, fp, fn, tn
+//   kind 1 (spatial) all elements, target y (0/1)                                   counts[0..3]
+//   kind 2 (dual)    presence head z[:, k] vs (y != -1), all elements               counts[0..3]
+//                    truth head z[:, Kpad + k] vs (y == 1) where y != -1            counts[4..7]
+//   kind 3 (3-class) argmax(z[:, 3k..3k+2]) (first maximum) vs y + 1                counts[3*target + pred], 9 entries
+// Y is the label matrix as stored ([n, *] int8), `keep` selects its K kept columns (nullptr: identity).
+__global__ void probe_confusion_kernel(const float* __restrict__ Z, long long ldz, const signed char* __restrict__ Y,
+                                       long long ldy, const int* __restrict__ keep, int n, int K, int Kpad, int kind,
+                                       float thresh, unsigned long long* __restrict__ counts) {
+  unsigned int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long total = static_cast<long long>(n) * K;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / K;
+    const int k = static_cast<int>(i - r * K);
+    const int y = Y[r * ldy + (keep ? keep[k] : k)];
+    if (kind == 3) {
+      const float* z = Z + r * ldz + 3 * k;
+      int pred = 0;
+      float best = z[0];
+      if (z[1] > best) { best = z[1]; pred = 1; }
+      if (z[2] > best) { pred = 2; }
+      c[3 * (y + 1) + pred]++;
+      continue;
+    }
+    auto sig = [](float z) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-z))); };
+    if (kind == 2) {
+      const int pt = (y != -1), pp = sig(Z[r * ldz + k]) > 0.5f;
+      c[pt ? (pp ? 0 : 2) : (pp ? 1 : 3)]++;
+      if (y != -1) {
+        const int tt = (y == 1), tp = sig(Z[r * ldz + Kpad + k]) > 0.5f;
+        c[4 + (tt ? (tp ? 0 : 2) : (tp ? 1 : 3))]++;
+      }
+      continue;
+    }
+    if (kind == 0 && y == -1) continue;
+    const int t = (kind == 0) ? (y == 1) : (y != 0), pr = sig(Z[r * ldz + k]) > thresh;
+    c[t ? (pr ? 0 : 2) : (pr ? 1 : 3)]++;
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    unsigned int v = c[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counts + j, static_cast<unsigned long long>(v));
+  }
+}
+
+int probe_confusion_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, const int* keep, int n,
+                           int K, int Kpad, int kind, float thresh, unsigned long long* counts, cudaStream_t st) {
+  if (kind < 0 || kind > 3) return set_error("probe confusion: unknown kind %d", kind);
+  CUDA_TRY(cudaMemsetAsync(counts, 0, 9 * sizeof(unsigned long long), st));
+  const long long total = static_cast<long long>(n) * K;
+  if (total <= 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+  probe_confusion_kernel<<<blocks, 256, 0, st>>>(Z, ldz, Y, ldy, keep, n, K, Kpad, kind, thresh, counts);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;

@@ -172,7 +172,8 @@ class OpenVLAForActionPrediction:
 
         c = self.config
         if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or tuple(frames_u8.shape[1:]) != (c.image_size, c.image_size, 3):
-            raise ValueError(f"frames must be uint8 [B, {c.image_size}, {c.image_size}, 3] (resize / crop are host-side input prep)")
+            raise ValueError(f"frames must be uint8 [B, {c.image_size}, {c.image_size}, 3] (see center_crop_frames; the "
+                             "lanczos resize of the simulator frame is host-side input prep)")
         names = ["dino", "siglip"] if c.use_fused_vision_backbone else ["siglip"]
         if not hasattr(self, "_norm_dev"):
             mean = torch.tensor([v for n in names for v in self._TOWER_STATS[n][0]], dtype=torch.float32)
@@ -185,6 +186,24 @@ class OpenVLAForActionPrediction:
             _lib.check(self.engine.lib.ovla_preprocess_frames(
                 C.c_void_p(fr.data_ptr()), B, c.image_size, len(names), C.c_void_p(self._norm_dev[0].data_ptr()),
                 C.c_void_p(self._norm_dev[1].data_ptr()), C.c_void_p(out.data_ptr()), _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def center_crop_frames(self, frames_u8: torch.Tensor, crop_scale: float = 0.9) -> torch.Tensor:
+        """The reference's `center_crop=True` branch (openvla_utils.py:155-175) on the device: uint8 HWC frames
+        [B, H, W, 3] -> centred square crop of area `crop_scale`, bilinear `tf.image.crop_and_resize` back to the model
+        resolution, uint8 [B, S, S, 3] (stays on the device: feed it to `preprocess_frames`)."""
+        import ctypes as C
+
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [B, H, W, 3]")
+        fr = frames_u8.to(self.device, non_blocking=True).contiguous()
+        B, H, W, _ = fr.shape
+        S = self.config.image_size
+        out = torch.empty(B, S, S, 3, dtype=torch.uint8, device=self.device)
+        if B:
+            _lib.check(self.engine.lib.ovla_center_crop_frames(
+                C.c_void_p(fr.data_ptr()), B, H, W, C.c_float(crop_scale), C.c_void_p(out.data_ptr()), S, _lib.stream_ptr()))
         return out
 
     # ------------------------------------------------------------------ public surface

@@ -71,11 +71,15 @@ def get_vla_action(vla, processor, base_vla_name, obs, task_label, unnorm_key, c
                    return_embeddings: bool = False):
     """openvla_utils.py:140-207.  `obs["full_image"]` is a uint8 HxWx3 frame.  Returns `action` (float64 [7]) or
     `(embeds, action)` with embeds = {layer_idx: float32 [4096]}."""
+    frame = obs["full_image"]
     if center_crop:
-        raise NotImplementedError("center_crop uses TensorFlow image ops (openvla_utils.py:155-175): input "
-                                  "preparation is outside this path; pass an already cropped frame")
+        # openvla_utils.py:155-175: crop scale 0.9 (side sqrt(0.9)), bilinear crop_and_resize back to 224 x 224, uint8;
+        # done by the CUDA kernel behind `vla.center_crop_frames` instead of TensorFlow
+        if not hasattr(vla, "center_crop_frames"):
+            raise NotImplementedError("center_crop needs a model object with `center_crop_frames`")
+        frame = vla.center_crop_frames(torch.from_numpy(np.ascontiguousarray(frame))[None], 0.9)[0].cpu().numpy()
     prompt = build_prompt(base_vla_name, task_label)
-    inputs = processor(prompt, obs["full_image"])
+    inputs = processor(prompt, frame)
     input_ids = inputs["input_ids"]
     pixel_values = inputs["pixel_values"].to(torch.bfloat16)       # `.to(DEVICE, dtype=torch.bfloat16)`, :186
     attention_mask = inputs.get("attention_mask")

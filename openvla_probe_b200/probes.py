@@ -428,7 +428,71 @@ class ProbeTrainer:
 
 
 # ----------------------------------------------------------------------------------------------- evaluation (host, as reference)
-def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, thresh: float = 0.5):
+def _f1_binary_macro(tp: int, fp: int, fn: int, tn: int) -> float:
+    """sklearn.metrics.f1_score(y_true, y_pred, average="macro", zero_division=0) from the confusion counts: per-class F1
+    over the classes that occur in y_true or y_pred (sklearn's default `labels`), undefined F1 counted as 0."""
+    f = []
+    if tp + fn + fp > 0:                                  # class 1 occurs in truth or prediction
+        f.append(2 * tp / (2 * tp + fp + fn))
+    if tn + fp + fn > 0:                                  # class 0 occurs
+        f.append(2 * tn / (2 * tn + fn + fp))
+    return float(sum(f) / len(f)) if f else 0.0
+
+
+def metrics_from_counts(kind: str, c: Sequence[int]) -> Dict[str, float]:
+    """Validation accuracy / F1 of the reference scripts from on-device confusion counts (ovla_probe_confusion)."""
+    c = [int(v) for v in c]
+    if kind == KIND_3CLASS:                               # train_3class_direct.py:196-207, labels=[0,1,2] macro
+        total = sum(c)
+        acc = (c[0] + c[4] + c[8]) / total if total else 0.0
+        f = []
+        for k in range(3):
+            tp = c[3 * k + k]
+            fp = sum(c[3 * t + k] for t in range(3)) - tp
+            fn = sum(c[3 * k + p] for p in range(3)) - tp
+            f.append(2 * tp / (2 * tp + fp + fn) if 2 * tp + fp + fn else 0.0)
+        return dict(val_acc=float(acc), val_f1=float(sum(f) / 3) if total else 0.0)
+    if kind == KIND_DUAL:                                 # train_dual_head_final.py:196-232
+        ptp, pfp, pfn, ptn, ttp, tfp, tfn, ttn = c[:8]
+        pn, tn_ = ptp + pfp + pfn + ptn, ttp + tfp + tfn + ttn
+        pres_f1 = 2 * ptp / (2 * ptp + pfp + pfn) if 2 * ptp + pfp + pfn else 0.0       # average="binary", pos_label=1
+        tf = [2 * ttn / (2 * ttn + tfn + tfp) if 2 * ttn + tfn + tfp else 0.0,          # labels=[0, 1], macro
+              2 * ttp / (2 * ttp + tfp + tfn) if 2 * ttp + tfp + tfn else 0.0]
+        return dict(pres_acc_va=(ptp + ptn) / pn if pn else 0.0, truth_acc_va=(ttp + ttn) / tn_ if tn_ else 0.0,
+                    pres_f1_va=float(pres_f1), truth_f1_va=float(sum(tf) / 2) if tn_ else 0.0)
+    tp, fp, fn, tn = c[:4]
+    n = tp + fp + fn + tn
+    if not n:
+        return dict(val_acc=0.0, val_f1=0.0)
+    return dict(val_acc=(tp + tn) / n, val_f1=_f1_binary_macro(tp, fp, fn, tn))
+
+
+def confusion_counts(kind: str, trainer: "ProbeTrainer", Z: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor,
+                     thresh: float = 0.5) -> List[int]:
+    """Confusion counts of device logits Z [n, rows] against int8 labels Y [n, *] (columns `keep`), on the device."""
+    dev = trainer.dev
+    Yd = Y.to(dev, torch.int8).contiguous()
+    kd = keep.to(dev, torch.int32).contiguous()
+    counts = torch.zeros(9, dtype=torch.int64, device=dev)
+    code = {KIND_OBJECT: 0, KIND_SPATIAL: 1, KIND_DUAL: 2, KIND_3CLASS: 3}[kind]
+    trainer._lib_mod.check(trainer.lib.ovla_probe_confusion(
+        C.c_void_p(Z.data_ptr()), C.c_longlong(Z.stride(0)), C.c_void_p(Yd.data_ptr()), C.c_longlong(Yd.stride(0)),
+        C.c_void_p(kd.data_ptr()), Z.shape[0], trainer.K, trainer.Kpad, code, C.c_float(thresh),
+        C.c_void_p(counts.data_ptr()), trainer._lib_mod.stream_ptr()))
+    return counts.cpu().tolist()
+
+
+def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, thresh: float = 0.5,
+             on_device: bool = False):
+    if on_device:
+        # accuracy / F1 from integer confusion counts computed next to the logits: only 9 integers leave the GPU.
+        # Average precision needs the sorted scores and stays on the sklearn path (on_device=False).
+        Z = trainer.logits(X.to(trainer.dev, torch.float32).contiguous())
+        return metrics_from_counts(kind, confusion_counts(kind, trainer, Z, Y, keep, thresh))
+    return _evaluate_host(kind, trainer, X, Y, keep, thresh)
+
+
+def _evaluate_host(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, thresh: float = 0.5):
     """Validation metrics exactly as the reference computes them on the host with sklearn
     (train_object_probes.py:190-206; train_dual_head_final.py:196-232); logits come from the device GEMM."""
     from sklearn.metrics import average_precision_score, f1_score

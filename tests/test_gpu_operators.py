@@ -457,3 +457,23 @@ def test_splitk_small_m_gemm(L, M, N, K, mode, expect_split):
     assert lib.ovla_launch_count() - before == (2 if expect_split else 1)
     ok, e = close_bf16(out, ref, ulps=3.0)
     assert ok, e
+
+
+@pytest.mark.parametrize("B,H,W,scale", [(3, 256, 256, 0.9), (1, 224, 224, 0.9), (2, 300, 200, 0.5), (2, 224, 224, 1.0),
+                                         (1, 97, 131, 0.9)])
+def test_center_crop_frames_bit_exact(L, B, H, W, scale):
+    """center_crop=True input branch (openvla_utils.py:155-175): the CUDA kernel and the oracle's float32 restatement of
+    tf.image.crop_and_resize + convert_image_dtype agree on every byte."""
+    _lib, lib = L
+    rng = np.random.default_rng(H * W + B)
+    img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    img[0, : H // 3] = np.linspace(0, 255, W, dtype=np.uint8)[None, :, None]      # smooth ramp: many rounding boundaries
+    ref = O.center_crop_frames(img, scale, 224)
+    src = torch.from_numpy(img).cuda()
+    out = torch.empty(B, 224, 224, 3, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ovla_center_crop_frames(P(src), B, H, W, C.c_float(scale), P(out), 224, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    if scale == 1.0 and (H, W) == (224, 224):
+        assert np.array_equal(ref, img)                                           # full box at native size is the identity
+

@@ -223,3 +223,33 @@ def test_3class_probe_steps_vs_autograd():
         for k, v in tr.state_dict().items():
             moved = (params[k].detach() - sd0[k]).norm()
             assert (v - params[k].detach()).norm() <= 0.05 * moved + 1e-6, k
+
+
+@pytest.mark.parametrize("kind", ["object", "spatial", "dual", "3class"])
+def test_on_device_validation_counters_match_host_metrics(kind):
+    """evaluate(on_device=True): confusion counts computed next to the logits (ovla_probe_confusion) give the same
+    accuracy / F1 as the reference's gather-to-host + sklearn path, and the counts themselves equal numpy's."""
+    from openvla_probe_b200.probes import ProbeTrainer, confusion_counts, evaluate
+
+    X, Y, keep = _data(N=900, D=128, L=29, seed=3, spatial=(kind == "spatial"))
+    K = len(keep)
+    pw = torch.tensor(1.7) if kind == "dual" else (torch.ones(3) if kind == "3class" else torch.full((K,), 1.3))
+    tr = ProbeTrainer(kind, 128, K, pw, batch=256, device=0)
+    tr.fit(X, Y, keep, epochs=2, seed=0)
+    host = evaluate(kind, tr, X, Y, keep)
+    dev = evaluate(kind, tr, X, Y, keep, on_device=True)
+    for k, v in dev.items():
+        assert abs(v - host[k]) < 1e-6, (k, v, host[k])      # the host path averages in fp32
+    Z = tr.logits(X.cuda().contiguous())
+    counts = confusion_counts(kind, tr, Z, Y, keep)
+    y = Y[:, keep].long().numpy()
+    z = Z.cpu().numpy()
+    if kind == "3class":
+        pred = z[:, :3 * K].reshape(-1, 3).argmax(1)
+        tgt = (y + 1).reshape(-1)
+        want = [int(((tgt == a) & (pred == b)).sum()) for a in range(3) for b in range(3)]
+        assert counts == want
+    elif kind == "dual":
+        assert sum(counts[:4]) == y.size and sum(counts[4:8]) == int((y != -1).sum())
+    else:
+        assert sum(counts[:4]) == (int((y != -1).sum()) if kind == "object" else y.size)

@@ -166,3 +166,21 @@ def test_tiny_dims_fp64_cross_check(tiny):
         o64 = O.multimodal_forward(W64, d, ids, px.double(), dtype=torch.float64)
     for a, b in zip(o32.hidden_states, o64.hidden_states):
         assert float((a.double() - b).abs().max()) < 1e-3 * float(b.abs().max())
+
+
+def test_center_crop_restatement_properties():
+    """center_crop input branch (openvla_utils.py:81-124,155-175): the full box at native size is the identity, a
+    constant frame stays constant, the crop is centred (commutes with a 180 degree rotation) and a 0.9-area crop of a
+    horizontal ramp keeps the ramp's centre value at the centre."""
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+    assert np.array_equal(O.center_crop_frames(img, 1.0), img)
+    assert np.unique(O.center_crop_frames(np.full((1, 256, 256, 3), 201, np.uint8), 0.9)).tolist() == [201]
+    a = O.center_crop_frames(img, 0.9)
+    b = O.center_crop_frames(img[:, ::-1, ::-1].copy(), 0.9)[:, ::-1, ::-1]
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1          # float32 lerp order differs by at most one code
+    ramp = np.broadcast_to(np.arange(256, dtype=np.uint8)[None, None, :, None], (1, 256, 256, 3)).copy()
+    out = O.center_crop_frames(ramp, 0.9)
+    side = np.sqrt(np.float32(0.9))
+    assert abs(int(out[0, 100, 0, 0]) - (1 - side) / 2 * 255) <= 1 and abs(int(out[0, 100, 223, 0]) - (1 + side) / 2 * 255) <= 1
+

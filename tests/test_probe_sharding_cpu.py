@@ -160,3 +160,32 @@ def test_packed_episode_store_round_trip(tmp_path):
     want = np.concatenate([p[1][2] for p in ref if p[0] == 1])
     assert np.array_equal(d["visual_semantic_encoding"][2].numpy(), want)
     assert d["symbolic_state_object_relations"].dtype == torch.int8 and d["symbolic_state_object_relations"].shape == (8, 5)
+
+
+def test_metrics_from_confusion_counts_match_sklearn():
+    """acc / F1 computed from integer confusion counts == the sklearn calls the reference makes on gathered arrays
+    (train_object_probes.py:190-206, train_dual_head_final.py:196-232, train_3class_direct.py:196-207)."""
+    from sklearn.metrics import f1_score
+
+    from openvla_probe_b200.probes import KIND_3CLASS, KIND_DUAL, KIND_OBJECT, KIND_SPATIAL, metrics_from_counts
+
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        n = 500
+        t = rng.integers(0, 2, n) if trial < 4 else np.zeros(n, dtype=np.int64)       # degenerate: a single class
+        p = rng.integers(0, 2, n) if trial != 5 else np.zeros(n, dtype=np.int64)
+        tp, fp = int(((p == 1) & (t == 1)).sum()), int(((p == 1) & (t == 0)).sum())
+        fn, tn = int(((p == 0) & (t == 1)).sum()), int(((p == 0) & (t == 0)).sum())
+        for kind in (KIND_OBJECT, KIND_SPATIAL):
+            m = metrics_from_counts(kind, [tp, fp, fn, tn])
+            assert abs(m["val_acc"] - float((p == t).mean())) < 1e-12
+            assert abs(m["val_f1"] - f1_score(t, p, average="macro", zero_division=0)) < 1e-12
+        m = metrics_from_counts(KIND_DUAL, [tp, fp, fn, tn, tp, fp, fn, tn])
+        assert abs(m["pres_f1_va"] - f1_score(t, p, average="binary", pos_label=1, zero_division=0)) < 1e-12
+        assert abs(m["truth_f1_va"] - f1_score(t, p, labels=[0, 1], average="macro", zero_division=0)) < 1e-12
+        assert abs(m["truth_acc_va"] - float((p == t).mean())) < 1e-12
+    t3, p3 = rng.integers(0, 3, 700), rng.integers(0, 3, 700)
+    conf = [int(((t3 == a) & (p3 == b)).sum()) for a in range(3) for b in range(3)]
+    m = metrics_from_counts(KIND_3CLASS, conf)
+    assert abs(m["val_acc"] - float((p3 == t3).mean())) < 1e-12
+    assert abs(m["val_f1"] - f1_score(t3, p3, labels=[0, 1, 2], average="macro", zero_division=0)) < 1e-12
