@@ -184,3 +184,90 @@ def test_center_crop_restatement_properties():
     side = np.sqrt(np.float32(0.9))
     assert abs(int(out[0, 100, 0, 0]) - (1 - side) / 2 * 255) <= 1 and abs(int(out[0, 100, 223, 0]) - (1 + side) / 2 * 255) <= 1
 
+
+
+def _tower_sd(W, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in W.items() if k.startswith(prefix + ".")}
+
+
+def test_vit_towers_match_independent_transformers_implementations():
+    """timm 0.9.10 (the reference's ViT code) cannot be installed here, so the oracle's tower arithmetic is pinned to
+    the OTHER public implementations of the same two architectures: transformers' Dinov2WithRegistersModel
+    (= vit_large_patch14_reg4_dinov2: cls + 4 register tokens, position embedding on the patches, LayerScale, erf-GELU)
+    and SiglipVisionModel (= vit_so400m_patch14_siglip with hidden_act="gelu", as timm 0.9.10 runs it).  Weights are
+    mapped name by name; the oracle's output (blocks 0..depth-2, prefix stripped, no final norm,
+    modeling_prismatic.py:85-87,119-123) equals hidden_states[depth-1] of the HF encoders."""
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel, SiglipVisionConfig, SiglipVisionModel
+
+    d = O.tiny_dims()
+    W = O.make_weights(d, seed=5, dtype=torch.float32)
+    img = torch.randn(2, 3, d.image_size, d.image_size)
+    np_ = d.n_patches
+
+    # ---- DINOv2 with registers
+    t = d.towers[0]
+    sd = _tower_sd(W, O.TOWER_PREFIX[0])
+    cfg = Dinov2WithRegistersConfig(hidden_size=t.dim, num_hidden_layers=t.depth, num_attention_heads=t.heads,
+                                    mlp_ratio=t.mlp // t.dim, hidden_act="gelu", layer_norm_eps=1e-6,
+                                    image_size=d.image_size, patch_size=d.patch, num_register_tokens=4, qkv_bias=True,
+                                    layerscale_value=1.0, use_swiglu_ffn=False, hidden_dropout_prob=0.0,
+                                    attention_probs_dropout_prob=0.0, drop_path_rate=0.0, attn_implementation="eager")
+    m = Dinov2WithRegistersModel(cfg).float().eval()
+    hs = {}
+    D = t.dim
+    hs["embeddings.cls_token"] = sd["cls_token"]
+    hs["embeddings.mask_token"] = torch.zeros(1, D)
+    hs["embeddings.register_tokens"] = sd["reg_token"]
+    hs["embeddings.position_embeddings"] = torch.cat([torch.zeros(1, 1, D), sd["pos_embed"]], 1)   # no_embed_class
+    hs["embeddings.patch_embeddings.projection.weight"] = sd["patch_embed.proj.weight"]
+    hs["embeddings.patch_embeddings.projection.bias"] = sd["patch_embed.proj.bias"]
+    for i in range(t.depth):
+        b, h = f"blocks.{i}.", f"encoder.layer.{i}."
+        for n in ("norm1", "norm2"):
+            hs[h + n + ".weight"], hs[h + n + ".bias"] = sd[b + n + ".weight"], sd[b + n + ".bias"]
+        qw, kw, vw = sd[b + "attn.qkv.weight"].chunk(3, 0)
+        qb, kb, vb = sd[b + "attn.qkv.bias"].chunk(3, 0)
+        for nm, w_, b_ in (("query", qw, qb), ("key", kw, kb), ("value", vw, vb)):
+            hs[h + f"attention.attention.{nm}.weight"], hs[h + f"attention.attention.{nm}.bias"] = w_, b_
+        hs[h + "attention.output.dense.weight"], hs[h + "attention.output.dense.bias"] = sd[b + "attn.proj.weight"], sd[b + "attn.proj.bias"]
+        hs[h + "layer_scale1.lambda1"], hs[h + "layer_scale2.lambda1"] = sd[b + "ls1.scale_factor"], sd[b + "ls2.scale_factor"]
+        for n in ("fc1", "fc2"):
+            hs[h + f"mlp.{n}.weight"], hs[h + f"mlp.{n}.bias"] = sd[b + f"mlp.{n}.weight"], sd[b + f"mlp.{n}.bias"]
+    hs["layernorm.weight"], hs["layernorm.bias"] = torch.ones(D), torch.zeros(D)
+    missing, unexpected = m.load_state_dict(hs, strict=False)
+    assert not unexpected and not [k for k in missing if "mask_token" not in k], (missing, unexpected)
+    with torch.no_grad():
+        ref = m(pixel_values=img, output_hidden_states=True).hidden_states[t.depth - 1][:, t.n_prefix:]
+        got = O.vit_tower(W, O.TOWER_PREFIX[0], t, d, img)
+    assert got.shape == ref.shape == (2, np_, D)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), float((got - ref).abs().max())
+
+    # ---- SigLIP
+    t = d.towers[1]
+    sd = _tower_sd(W, O.TOWER_PREFIX[1])
+    D = t.dim
+    cfg = SiglipVisionConfig(hidden_size=D, intermediate_size=t.mlp, num_hidden_layers=t.depth, num_attention_heads=t.heads,
+                             image_size=d.image_size, patch_size=d.patch, hidden_act="gelu", layer_norm_eps=1e-6,
+                             attention_dropout=0.0, attn_implementation="eager")
+    m = SiglipVisionModel(cfg).float().eval()
+    hs = {"vision_model.embeddings.patch_embedding.weight": sd["patch_embed.proj.weight"],
+          "vision_model.embeddings.patch_embedding.bias": sd["patch_embed.proj.bias"],
+          "vision_model.embeddings.position_embedding.weight": sd["pos_embed"][0]}
+    for i in range(t.depth):
+        b, h = f"blocks.{i}.", f"vision_model.encoder.layers.{i}."
+        hs[h + "layer_norm1.weight"], hs[h + "layer_norm1.bias"] = sd[b + "norm1.weight"], sd[b + "norm1.bias"]
+        hs[h + "layer_norm2.weight"], hs[h + "layer_norm2.bias"] = sd[b + "norm2.weight"], sd[b + "norm2.bias"]
+        qw, kw, vw = sd[b + "attn.qkv.weight"].chunk(3, 0)
+        qb, kb, vb = sd[b + "attn.qkv.bias"].chunk(3, 0)
+        for nm, w_, b_ in (("q_proj", qw, qb), ("k_proj", kw, kb), ("v_proj", vw, vb)):
+            hs[h + f"self_attn.{nm}.weight"], hs[h + f"self_attn.{nm}.bias"] = w_, b_
+        hs[h + "self_attn.out_proj.weight"], hs[h + "self_attn.out_proj.bias"] = sd[b + "attn.proj.weight"], sd[b + "attn.proj.bias"]
+        for n in ("fc1", "fc2"):
+            hs[h + f"mlp.{n}.weight"], hs[h + f"mlp.{n}.bias"] = sd[b + f"mlp.{n}.weight"], sd[b + f"mlp.{n}.bias"]
+    missing, unexpected = m.load_state_dict(hs, strict=False)
+    assert not unexpected and all(("post_layernorm" in k or ".head." in k) for k in missing), (missing, unexpected)
+    with torch.no_grad():
+        ref = m(pixel_values=img, output_hidden_states=True).hidden_states[t.depth - 1]
+        got = O.vit_tower(W, O.TOWER_PREFIX[1], t, d, img)
+    assert got.shape == ref.shape == (2, np_, D)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), float((got - ref).abs().max())
