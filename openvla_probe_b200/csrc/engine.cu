@@ -639,7 +639,10 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     CUDA_TRY(cudaEventRecord(e->ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
     OVLA_TRY(run_tower(e, 0, px, B, e->vb[0], st));
-    OVLA_TRY(run_tower(e, 1, px, B, e->vb[1], e->side_stream));
+    set_splitk_slot(1);   // the towers overlap in time: the side stream's split-K GEMMs get their own partial-tile buffer
+    const int rc_side = run_tower(e, 1, px, B, e->vb[1], e->side_stream);
+    set_splitk_slot(0);
+    if (rc_side) return rc_side;
     CUDA_TRY(cudaEventRecord(e->ev_join, e->side_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
   } else {

@@ -15,6 +15,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
                 const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream);
 // splitk.cu -- split-K workspace + reduce/epilogue
 float* splitk_workspace();
+void set_splitk_slot(int slot);  // workspace used by the GEMMs issued next from this thread (0 main stream, 1 side stream)
 long long splitk_workspace_floats();
 int splitk_epilogue_launch(int mode, const float* ws, long long slice_stride, long long ldw, int S, int M, int N,
                            const GemmEpi& epi, cudaStream_t st);

@@ -10,19 +10,27 @@
 namespace ovla {
 
 static constexpr long long kSplitWsFloats = 48LL << 20;  // 192 MB, allocated once (never re-allocated: CUDA graphs keep the pointer)
-static float* g_split_ws[16] = {};
+static constexpr int kSplitSlots = 2;                    // one workspace per concurrently running stream of an engine
+static float* g_split_ws[16][kSplitSlots] = {};
+static thread_local int g_split_slot = 0;
+
+// GEMMs issued between set_splitk_slot(s) calls use workspace s.  The engine runs its two vision towers on two
+// streams at small batch: their split-K GEMMs overlap in time (always under CUDA-graph replay), so each stream needs
+// its own partial-tile buffer.
+void set_splitk_slot(int slot) { g_split_slot = (slot >= 0 && slot < kSplitSlots) ? slot : 0; }
 
 float* splitk_workspace() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16) return nullptr;
-  if (!g_split_ws[dev]) {
-    if (cudaMalloc(&g_split_ws[dev], kSplitWsFloats * sizeof(float)) != cudaSuccess) {
+  float*& ws = g_split_ws[dev][g_split_slot];
+  if (!ws) {
+    if (cudaMalloc(&ws, kSplitWsFloats * sizeof(float)) != cudaSuccess) {
       cudaGetLastError();
-      g_split_ws[dev] = nullptr;
+      ws = nullptr;
     }
   }
-  return g_split_ws[dev];
+  return ws;
 }
 long long splitk_workspace_floats() { return kSplitWsFloats; }
 

@@ -179,3 +179,43 @@ def test_full_width_shapes_against_fp32_oracle():
         assert rel_l2(pooled[i], ref) < 1.5e-2, i
     assert rel_l2(r["step_logits"][0].cpu(), out.logits[:, -1]) < 3e-2
     assert torch.equal(r["tokens"].cpu(), torch.argmax(r["step_logits"].cpu(), -1).t())
+
+
+def test_full_size_7b_size_independent_properties():
+    """BASELINE config [2] at full size (24 + 27 ViT blocks, 32 Llama layers, 224 px, real widths; random-init weights
+    as in bench.py -- the CPU oracle cannot run this in test time), checked through properties that do not need it:
+    run-to-run determinism (bit-identical), batch invariance of the captured states (a row computed alone -- CUDA-graph
+    replay, GEMV decode, split-K GEMMs -- against the same row inside a batch of three on the tensor-core tiles),
+    host and device entry points agreeing bit for bit, pooling semantics, and actions inside the un-normalisation box."""
+    import dataclasses
+
+    from bench import synthetic_inputs
+    from openvla_probe_b200 import config as cfgmod, weights
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    stats = {"synthetic": {"action": {"q01": [-1.0] * 7, "q99": [2.0] * 7}}}
+    cfg = dataclasses.replace(cfgmod.openvla_7b(), norm_stats=stats)
+    model = OpenVLAForActionPrediction(cfg, max_batch=3, max_prompt_len=24)
+    weights.bind_random(model)
+    ids, px = synthetic_inputs(cfg, 3, 20, 7)
+    L, D = cfg.text_config.num_hidden_layers, cfg.text_config.hidden_size
+
+    (a3, t3), p3 = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda(), return_tokens=True)
+    (a3b, t3b), p3b = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda(), return_tokens=True)
+    assert p3.shape == (L + 1, 3, D) and np.isfinite(p3).all()
+    assert np.array_equal(t3, t3b) and np.array_equal(p3, p3b) and np.array_equal(a3, a3b)          # deterministic
+    (ah, th), ph = model._predict(ids, "synthetic", capture=True, pixel_values=px, return_tokens=True)
+    assert np.array_equal(th, t3) and np.array_equal(ph, p3)                                         # host == device entry
+    assert ((a3 >= -1.0 - 1e-9) & (a3 <= 2.0 + 1e-9)).all() and a3.shape == (3, 7)
+
+    for b in range(3):
+        for _ in range(3):                                   # third call replays the captured CUDA graph
+            (a1, t1), p1 = model._predict(ids[b:b + 1].cuda(), "synthetic", capture=True, pixel_values=px[b:b + 1].cuda(),
+                                          return_tokens=True)
+        for layer in (0, 1, 8, 16, 24, L):
+            err = np.linalg.norm(p1[layer, 0] - p3[layer, b]) / np.linalg.norm(p3[layer, b])
+            assert err < 2e-2, (b, layer, err)               # same math, different tiling / reduction order in bf16
+    # layer 0 is the embedding stream (BOS | projected patches | text): pooling fewer rows changes it, "final" != "mean"
+    _, p_final = model._predict(ids.cuda(), "synthetic", capture=True, pooling_method="final", pixel_values=px.cuda())
+    assert not np.allclose(p_final[0], p3[0]) and np.isfinite(p_final).all()
+    model.engine.close()
