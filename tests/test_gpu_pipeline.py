@@ -227,3 +227,33 @@ def test_full_size_7b_size_independent_properties():
     _, p_final = model._predict(ids.cuda(), "synthetic", capture=True, pooling_method="final", pixel_values=px.cuda())
     assert not np.allclose(p_final[0], p3[0]) and np.isfinite(p_final).all()
     model.engine.close()
+
+
+def test_full_size_siglip_single_backbone_properties():
+    """BASELINE config [4] at full size (SigLIP SO400M only, 2-layer projector, 32 Llama layers): the single-backbone
+    wiring (modeling_prismatic.py:135-137,148-150) with head_dim-72 attention -- determinism and a row alone (CUDA-graph
+    replay) against the same row in a batch."""
+    import dataclasses
+
+    from bench import synthetic_inputs
+    from openvla_probe_b200 import config as cfgmod, weights
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    stats = {"synthetic": {"action": {"q01": [0.0] * 7, "q99": [1.0] * 7}}}
+    cfg = dataclasses.replace(cfgmod.siglip_7b(), norm_stats=stats)
+    model = OpenVLAForActionPrediction(cfg, max_batch=4, max_prompt_len=24)
+    weights.bind_random(model)
+    ids, px = synthetic_inputs(cfg, 4, 18, 3)
+    assert px.shape[1] == 3                                              # one tower: 3 channels
+    L = cfg.text_config.num_hidden_layers
+    (a4, t4), p4 = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda(), return_tokens=True)
+    (a4b, t4b), p4b = model._predict(ids.cuda(), "synthetic", capture=True, pixel_values=px.cuda(), return_tokens=True)
+    assert np.array_equal(t4, t4b) and np.array_equal(p4, p4b) and np.isfinite(p4).all()
+    for b in (0, 3):
+        for _ in range(3):
+            (a1, t1), p1 = model._predict(ids[b:b + 1].cuda(), "synthetic", capture=True, pixel_values=px[b:b + 1].cuda(),
+                                          return_tokens=True)
+        for layer in (0, 1, 16, L):
+            err = np.linalg.norm(p1[layer, 0] - p4[layer, b]) / np.linalg.norm(p4[layer, b])
+            assert err < 2e-2, (b, layer, err)
+    model.engine.close()

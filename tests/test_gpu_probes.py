@@ -253,3 +253,48 @@ def test_on_device_validation_counters_match_host_metrics(kind):
         assert sum(counts[:4]) == y.size and sum(counts[4:8]) == int((y != -1).sum())
     else:
         assert sum(counts[:4]) == (int((y != -1).sum()) if kind == "object" else y.size)
+
+
+def test_full_size_object_probe_step_vs_autograd():
+    """BASELINE config [3] at full size: batch 4096 x 4096-d features x 439 kept labels (461 + 20 minus 42 dropped),
+    one object-probe step against fp32 autograd (run on the GPU with TF32 disabled as the checker), same tolerances as
+    the small-shape test: logits / dW rel-L2 <= 2e-3, loss <= 1e-3 relative."""
+    from openvla_probe_b200.probes import ProbeTrainer
+
+    N, D, Lbl = 4096, 4096, 481
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(N, D, generator=g)
+    Y = torch.randint(-1, 2, (N, Lbl), generator=g).to(torch.int8)
+    keep = torch.tensor(sorted(np.random.default_rng(2).choice(Lbl, size=439, replace=False).tolist()))
+    K = len(keep)
+    pw = 0.5 + 3 * torch.rand(K, generator=g)
+    torch.manual_seed(3)
+    tr = ProbeTrainer("object", D, K, pw, batch=N)
+    sd0 = tr.state_dict()
+    perm = torch.arange(N)
+    tr.load_epoch(X.cuda(), Y.cuda(), keep, perm, drop_last=False)
+    assert len(tr.steps) == 1
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Wr = sd0["weight"].cuda().clone().requires_grad_(True)
+        br = sd0["bias"].cuda().clone().requires_grad_(True)
+        Xd, Yk = X.cuda(), Y[:, keep].cuda()
+        z_ref = Xd @ Wr.t() + br
+        mask = (Yk != -1)
+        el = torch.nn.functional.binary_cross_entropy_with_logits(z_ref, (Yk == 1).float(), pos_weight=pw.cuda(), reduction="none")
+        loss_ref = (el * mask.float()).sum() / mask.sum()
+        loss_ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    z = tr.logits(Xd)[:, :K]
+    assert float((z - z_ref.detach()).norm() / z_ref.detach().norm()) < 2e-3
+    tr.train_step(0)
+    assert abs(tr.step_loss() - float(loss_ref.detach())) <= 1e-3 * abs(float(loss_ref.detach()))
+    G = tr.G
+    cnt = G[tr.n_total + 1]
+    dW = G[: tr.n_w].view(tr.rows, D)[:K] / cnt
+    db = G[tr.n_w: tr.n_total][:K] / cnt
+    assert float((dW - Wr.grad).norm() / Wr.grad.norm()) < 2e-3
+    assert float((db - br.grad).norm() / br.grad.norm()) < 2e-3
+    assert int(cnt.item()) == int(mask.sum().item())
