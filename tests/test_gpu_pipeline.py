@@ -268,3 +268,51 @@ def test_full_size_siglip_single_backbone_properties():
             err = np.linalg.norm(p1[layer, 0] - p4[layer, b]) / np.linalg.norm(p4[layer, b])
             assert err < 2e-2, (b, layer, err)
     model.engine.close()
+
+
+def test_full_size_single_observation_against_fp32_oracle():
+    """BASELINE config [1]/[2] at FULL size -- every ViT block, 32 Llama layers, real widths, 224-px frame, T = 277 --
+    for one observation against the CPU oracle in fp32 on identical (bf16-representable) weights.  Stated tolerance:
+    rel-L2 <= 1.5e-2 on each of the 33 mean-pooled hidden states, <= 2.5e-2 on the vision / projector outputs (a bf16
+    pipeline ~300 rounding points deep against fp32), <= 6e-2 on the last-position logits (measured: 0.16-0.81 % on the
+    pooled states growing with depth, 1.3 % vision / projector, 2.9 % logits).  Weights are drawn on the GPU and
+    copied to the host (30 GB fp32); skipped when the host has less than 48 GB of free memory."""
+    import dataclasses
+
+    import psutil
+
+    if psutil.virtual_memory().available < 48e9:
+        pytest.skip("needs 48 GB of free host memory for the fp32 oracle weights")
+    from openvla_probe_b200.modeling_prismatic import from_state_dict
+
+    od, pc = pair("openvla-7b")
+    pc = dataclasses.replace(pc, norm_stats={"synthetic": {"action": O.default_stats()}})
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    W = {}
+    for name, shape in O.weight_shapes(od).items():        # same init rules as O.make_weights, drawn on the device
+        affine = name.endswith(("norm1.weight", "norm2.weight", "layernorm.weight", "model.norm.weight", "scale_factor"))
+        w = torch.randn(shape, device="cuda", generator=g)
+        w = (1.0 + 0.1 * w) if affine else 0.02 * w
+        if name.endswith("embed_tokens.weight"):
+            w[od.pad_token_id] = 0.0
+        W[name] = w.to(torch.bfloat16).float().cpu()         # bf16-representable fp32 on the host
+    model = from_state_dict(pc, W, max_batch=1, max_prompt_len=24)
+    ids, px = O.make_inputs(od, 1, prompt_len=20, seed=3)
+    ids29 = torch.cat([ids, torch.full((1, 1), 29871)], 1)
+    pool_len = od.n_patches + 20
+    r = model.engine.run(ids29, px, pool_len, 0, 1, want_logits=True, want_patches=True, want_projector=True)
+    torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+    with torch.no_grad():
+        patches = O.vision_backbone(W, od, px.float())
+        out = O.multimodal_forward(W, od, ids29, px, dtype=torch.float32)
+    errs = {"patches": rel_l2(r["patches"].float().cpu(), patches),
+            "projector": rel_l2(r["projector"].float().cpu(), out.projector_features)}
+    pooled = r["pooled"].cpu()
+    for i, h in enumerate(out.hidden_states):
+        errs[f"pooled[{i}]"] = rel_l2(pooled[i], h[:, :pool_len].mean(1))
+    errs["logits"] = rel_l2(r["step_logits"][0].cpu(), out.logits[:, -1])
+    print("full-size rel-L2 vs fp32 oracle:", {k: round(v, 5) for k, v in errs.items()})
+    assert len(out.hidden_states) == 33
+    for k, v in errs.items():
+        assert v < (6e-2 if k == "logits" else 1.5e-2 if k.startswith("pooled") else 2.5e-2), (k, v)
+    model.engine.close()
