@@ -275,7 +275,8 @@ def test_full_size_single_observation_against_fp32_oracle():
     for one observation against the CPU oracle in fp32 on identical (bf16-representable) weights.  Stated tolerance:
     rel-L2 <= 1.5e-2 on each of the 33 mean-pooled hidden states, <= 2.5e-2 on the vision / projector outputs (a bf16
     pipeline ~300 rounding points deep against fp32), <= 6e-2 on the last-position logits (measured: 0.16-0.81 % on the
-    pooled states growing with depth, 1.3 % vision / projector, 2.9 % logits).  Weights are drawn on the GPU and
+    pooled states growing with depth, 1.3 % vision / projector, 2.9 % logits); the 6 cached decode steps are compared
+    the same way, teacher-forced with the device's own tokens.  Weights are drawn on the GPU and
     copied to the host (30 GB fp32); skipped when the host has less than 48 GB of free memory."""
     import dataclasses
 
@@ -300,7 +301,7 @@ def test_full_size_single_observation_against_fp32_oracle():
     ids, px = O.make_inputs(od, 1, prompt_len=20, seed=3)
     ids29 = torch.cat([ids, torch.full((1, 1), 29871)], 1)
     pool_len = od.n_patches + 20
-    r = model.engine.run(ids29, px, pool_len, 0, 1, want_logits=True, want_patches=True, want_projector=True)
+    r = model.engine.run(ids29, px, pool_len, 0, 7, want_logits=True, want_patches=True, want_projector=True)
     torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
     with torch.no_grad():
         patches = O.vision_backbone(W, od, px.float())
@@ -311,8 +312,22 @@ def test_full_size_single_observation_against_fp32_oracle():
     for i, h in enumerate(out.hidden_states):
         errs[f"pooled[{i}]"] = rel_l2(pooled[i], h[:, :pool_len].mean(1))
     errs["logits"] = rel_l2(r["step_logits"][0].cpu(), out.logits[:, -1])
+    # the 6 cached decode steps (GEMV linears, fused RoPE + KV append + attention), teacher-forced with OUR tokens so that
+    # a near-tie flip cannot desynchronise the two sequences
+    toks = r["tokens"].cpu()                                  # [1, 7]
+    step_logits = r["step_logits"].cpu()                      # [7, 1, V]
+    assert torch.equal(toks, torch.argmax(step_logits, -1).t())
+    past = out.past_key_values
+    with torch.no_grad():
+        for k in range(1, 7):
+            o = O.cached_forward(W, od, toks[:, k - 1:k], past, torch.float32)
+            past = o.past_key_values
+            errs[f"decode_logits[{k}]"] = rel_l2(step_logits[k], o.logits[:, -1])
+            top2 = torch.topk(o.logits[0, -1], 2).values
+            if float(top2[0] - top2[1]) > 4 * float((step_logits[k, 0] - o.logits[0, -1]).abs().max()):
+                assert int(toks[0, k]) == int(torch.argmax(o.logits[0, -1]))     # clear margin -> same greedy token
     print("full-size rel-L2 vs fp32 oracle:", {k: round(v, 5) for k, v in errs.items()})
     assert len(out.hidden_states) == 33
     for k, v in errs.items():
-        assert v < (6e-2 if k == "logits" else 1.5e-2 if k.startswith("pooled") else 2.5e-2), (k, v)
+        assert v < (6e-2 if "logits" in k else 1.5e-2 if k.startswith("pooled") else 2.5e-2), (k, v)
     model.engine.close()
