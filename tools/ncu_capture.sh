@@ -9,10 +9,12 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/${R}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${R}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:ovla:: -s $N -c $N --csv \
     --log-file gpurun_out/${R}_launches.csv $CMD > gpurun_out/${R}_ncu_launches.log 2>&1
+if [ "$NCU_LIGHT" != "2" ]; then
 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 210 -c 4 \
     -o gpurun_out/${R}_gemm -f $CMD > gpurun_out/${R}_ncu_gemm.log 2>&1
+fi
 if [ -n "$NCU_LIGHT" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 26 -c 2 \
+  ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 22 -c 3 \
       -o gpurun_out/${R}_attn_tc -f $CMD > gpurun_out/${R}_ncu_attn_tc.log 2>&1
   ls -la gpurun_out/ | grep ${R}_ | tail -20
   exit 0
