@@ -787,7 +787,15 @@ extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const voi
   a.n_new_tokens = tokens_host ? n_new : 0;
   a.tokens_out_dev = e->out_tokens;
   // eager passes (no CUDA graph: B above the graph limit or graphs disabled) stream the pooled states out layer by layer
-  const bool stream_pooled = a.pool_len > 0 && !graph_eligible(e, &a);
+  // (only into page-locked memory: an async copy into pageable memory blocks the host until the pooling kernel it waits
+  // for has run, which would serialise kernel submission behind the device)
+  bool host_pinned = false;
+  if (pooled_host) {
+    cudaPointerAttributes pa = {};
+    if (cudaPointerGetAttributes(&pa, pooled_host) == cudaSuccess) host_pinned = pa.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  const bool stream_pooled = a.pool_len > 0 && host_pinned && !graph_eligible(e, &a);
   if (stream_pooled) {
     if (!e->copy_stream) {
       CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
