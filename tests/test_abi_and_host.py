@@ -139,3 +139,42 @@ def test_synthetic_processor_and_prompt():
     with pytest.raises(AssertionError):
         pool_tokens(torch.zeros(2, 3, 4))
     assert pool_tokens(torch.ones(1, 3, 4), "final").shape == (4,)
+
+
+def test_get_vla_action_center_crop_wiring():
+    """`center_crop=True` (openvla_utils.py:155-175): the frame goes through the model object's `center_crop_frames`
+    (crop scale 0.9) before the processor, and the cropped uint8 frame is what gets normalised.  A fake model backed by
+    the oracle's restatement stands in for the CUDA kernel here; the kernel itself is compared byte for byte on the GPU."""
+    from oracle import openvla_oracle as O
+    from openvla_probe_b200 import config
+    from openvla_probe_b200.openvla_utils import SyntheticProcessor, get_vla_action
+
+    class Fake:
+        def __init__(self):
+            self.seen = None
+
+        def center_crop_frames(self, frames, scale):
+            assert frames.dtype == torch.uint8 and frames.dim() == 4 and abs(scale - 0.9) < 1e-12
+            return torch.from_numpy(O.center_crop_frames(frames.numpy(), scale, 56))
+
+        def predict_action(self, input_ids, unnorm_key=None, pixel_values=None, **kw):
+            self.seen = pixel_values
+            return np.zeros(7)
+
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, (56, 56, 3), dtype=np.uint8)
+    proc = SyntheticProcessor(config.tiny(), prompt_len=9)
+    vla = Fake()
+    get_vla_action(vla, proc, "openvla", {"full_image": frame}, "do it", "k", center_crop=True)
+    cropped = O.center_crop_frames(frame[None], 0.9, 56)[0]
+    want = proc("x", cropped)["pixel_values"].to(torch.bfloat16)
+    assert torch.equal(vla.seen, want) and not np.array_equal(cropped, frame)
+    vla2 = Fake()
+    get_vla_action(vla2, proc, "openvla", {"full_image": frame}, "do it", "k", center_crop=False)
+    assert torch.equal(vla2.seen, proc("x", frame)["pixel_values"].to(torch.bfloat16))
+
+    class NoCrop:
+        pass
+
+    with pytest.raises(NotImplementedError):
+        get_vla_action(NoCrop(), proc, "openvla", {"full_image": frame}, "do it", "k", center_crop=True)
