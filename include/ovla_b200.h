@@ -206,6 +206,11 @@ int ovla_probe_ce3_grad(const float* z_dev, long long ldz, const signed char* yp
  * Binary layout: tp, fp, fn, tn.  y: int8 [n, *] with `keep_dev` (int32 [K], may be NULL) selecting its columns.   */
 int ovla_probe_confusion(const float* z_dev, long long ldz, const signed char* y_dev, long long ldy, const int* keep_dev,
                          int n, int K, int Kpad, int kind, float thresh, unsigned long long* counts9_dev, void* stream);
+/* Per-label counts for eval_probes_per_label.py:59-96 (mask y != -1, target y == 1, pred sigmoid(z) > thresh):
+ * counts_k4_dev[k*4 + {tp, fp, fn, tn}] for each kept label k (uint64 [K, 4]).                                     */
+int ovla_probe_confusion_per_label(const float* z_dev, long long ldz, const signed char* y_dev, long long ldy,
+                                   const int* keep_dev, int n, int K, float thresh, unsigned long long* counts_k4_dev,
+                                   void* stream);
 /* out[r] = sum_c a[r, c]  (bias gradient from dzt) */
 int ovla_probe_rowsum(const float* a_dev, long long lda, int rows, int cols, float* out_dev, void* stream);
 /* torch.optim.AdamW step on the flat [W (rows x D) | b (rows)] buffer; gradient rows of head h are divided by

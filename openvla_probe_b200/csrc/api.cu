@@ -122,6 +122,11 @@ int ovla_probe_confusion(const float* z, long long ldz, const signed char* y, lo
   if (!z || !y || !counts9) return set_error("ovla_probe_confusion: null buffer");
   return probe_confusion_launch(z, ldz, y, ldy, keep, n, K, Kpad, kind, thresh, counts9, static_cast<cudaStream_t>(stream));
 }
+int ovla_probe_confusion_per_label(const float* z, long long ldz, const signed char* y, long long ldy, const int* keep,
+                                   int n, int K, float thresh, unsigned long long* counts_k4, void* stream) {
+  if (!z || !y || !counts_k4) return set_error("ovla_probe_confusion_per_label: null buffer");
+  return probe_confusion_per_label_launch(z, ldz, y, ldy, keep, n, K, thresh, counts_k4, static_cast<cudaStream_t>(stream));
+}
 int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
                                void* kc, void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
                                void* stream) {

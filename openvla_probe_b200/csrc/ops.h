@@ -85,5 +85,7 @@ int probe_ce3_grad_launch(const float* Z, long long ldz, const signed char* Y, l
                           cudaStream_t st);
 int probe_confusion_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, const int* keep, int n,
                            int K, int Kpad, int kind, float thresh, unsigned long long* counts, cudaStream_t st);
+int probe_confusion_per_label_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, const int* keep,
+                                     int n, int K, float thresh, unsigned long long* counts, cudaStream_t st);
 
 }  // namespace ovla

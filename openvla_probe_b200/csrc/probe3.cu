@@ -153,4 +153,46 @@ int probe_confusion_launch(const float* Z, long long ldz, const signed char* Y, 
   return 0;
 }
 
+// Per-label confusion counts for the reference's per-label evaluation (experiment_utils/eval_probes_per_label.py:59-96:
+// for each kept label, mask y != -1, target y == 1, pred sigmoid(z) > 0.5, then precision / recall / F1 / MCC / balanced
+// accuracy -- all functions of these four integers).  One block per label; counts[k*4 + {tp, fp, fn, tn}].
+__global__ void __launch_bounds__(256) probe_confusion_per_label_kernel(
+    const float* __restrict__ Z, long long ldz, const signed char* __restrict__ Y, long long ldy,
+    const int* __restrict__ keep, int n, int K, float thresh, unsigned long long* __restrict__ counts) {
+  const int k = blockIdx.x;
+  if (k >= K) return;
+  const int col = keep ? keep[k] : k;
+  unsigned int c[4] = {0, 0, 0, 0};
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int y = Y[static_cast<long long>(r) * ldy + col];
+    if (y == -1) continue;
+    const float z = Z[static_cast<long long>(r) * ldz + k];
+    const int t = (y == 1), pr = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-z))) > thresh;
+    c[t ? (pr ? 0 : 2) : (pr ? 1 : 3)]++;
+  }
+  __shared__ unsigned int sm[4][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned int v = c[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long s2 = 0;
+    for (int w = 0; w < 8; ++w) s2 += sm[threadIdx.x][w];
+    counts[static_cast<long long>(k) * 4 + threadIdx.x] = s2;
+  }
+}
+
+int probe_confusion_per_label_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, const int* keep,
+                                     int n, int K, float thresh, unsigned long long* counts, cudaStream_t st) {
+  if (K <= 0) return 0;
+  probe_confusion_per_label_kernel<<<K, 256, 0, st>>>(Z, ldz, Y, ldy, keep, n, K, thresh, counts);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace ovla

@@ -482,6 +482,44 @@ def confusion_counts(kind: str, trainer: "ProbeTrainer", Z: torch.Tensor, Y: tor
     return counts.cpu().tolist()
 
 
+def per_label_counts(trainer: "ProbeTrainer", Z: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor,
+                     thresh: float = 0.5) -> np.ndarray:
+    """int64 [K, 4] (tp, fp, fn, tn) per kept label, counted on the device (mask y != -1, target y == 1)."""
+    dev = trainer.dev
+    Yd = Y.to(dev, torch.int8).contiguous()
+    kd = keep.to(dev, torch.int32).contiguous()
+    counts = torch.zeros(trainer.K, 4, dtype=torch.int64, device=dev)
+    trainer._lib_mod.check(trainer.lib.ovla_probe_confusion_per_label(
+        C.c_void_p(Z.data_ptr()), C.c_longlong(Z.stride(0)), C.c_void_p(Yd.data_ptr()), C.c_longlong(Yd.stride(0)),
+        C.c_void_p(kd.data_ptr()), Z.shape[0], trainer.K, C.c_float(thresh), C.c_void_p(counts.data_ptr()),
+        trainer._lib_mod.stream_ptr()))
+    return counts.cpu().numpy()
+
+
+def per_label_metrics(counts: np.ndarray, keep: Sequence[int]) -> List[Dict[str, float]]:
+    """eval_probes_per_label.py:77-96 from per-label confusion counts: sklearn's precision / recall / F1
+    (average="binary", zero_division=0), matthews_corrcoef and balanced_accuracy_score (NaN when the masked target holds
+    a single class); labels whose mask is empty are skipped, as in the reference."""
+    out = []
+    for k, (tp, fp, fn, tn) in enumerate(np.asarray(counts, dtype=np.int64).tolist()):
+        n = tp + fp + fn + tn
+        if n == 0:
+            continue
+        prec = tp / (tp + fp) if tp + fp else 0.0
+        rec = tp / (tp + fn) if tp + fn else 0.0
+        f1 = 2 * tp / (2 * tp + fp + fn) if 2 * tp + fp + fn else 0.0
+        both = (tp + fn) > 0 and (tn + fp) > 0                        # len(np.unique(targ)) > 1
+        if both:
+            den = float(tp + fp) * float(tp + fn) * float(tn + fp) * float(tn + fn)
+            mcc = (float(tp) * tn - float(fp) * fn) / den ** 0.5 if den > 0 else 0.0
+            bal = 0.5 * (tp / (tp + fn) + tn / (tn + fp))
+        else:
+            mcc = bal = float("nan")
+        out.append(dict(label_idx=int(keep[k]), prec=float(prec), recall=float(rec), f1=float(f1), mcc=float(mcc),
+                        bal_acc=float(bal)))
+    return out
+
+
 def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, thresh: float = 0.5,
              on_device: bool = False):
     if on_device:

@@ -298,3 +298,26 @@ def test_full_size_object_probe_step_vs_autograd():
     assert float((dW - Wr.grad).norm() / Wr.grad.norm()) < 2e-3
     assert float((db - br.grad).norm() / br.grad.norm()) < 2e-3
     assert int(cnt.item()) == int(mask.sum().item())
+
+
+def test_per_label_confusion_counts_on_device():
+    """ovla_probe_confusion_per_label: [K, 4] counts (tp, fp, fn, tn) of every kept label equal numpy's on the same
+    logits (eval_probes_per_label.py:59-96 semantics: mask y != -1, target y == 1, pred sigmoid(z) > 0.5)."""
+    from openvla_probe_b200.probes import ProbeTrainer, per_label_counts, per_label_metrics
+
+    X, Y, keep = _data(N=777, D=128, L=33, seed=5)
+    K = len(keep)
+    tr = ProbeTrainer("object", 128, K, torch.full((K,), 1.5), batch=256, device=0)
+    tr.fit(X, Y, keep, epochs=1, seed=0)
+    Z = tr.logits(X.cuda().contiguous())
+    counts = per_label_counts(tr, Z, Y, keep)
+    z = Z[:, :K].cpu()
+    pred = (torch.sigmoid(z) > 0.5).numpy()
+    y = Y[:, keep].numpy()
+    want = np.zeros((K, 4), dtype=np.int64)
+    for k in range(K):
+        m = y[:, k] != -1
+        t, q = y[m, k] == 1, pred[m, k]
+        want[k] = [(t & q).sum(), (~t & q).sum(), (t & ~q).sum(), (~t & ~q).sum()]
+    assert counts.shape == (K, 4) and np.array_equal(counts, want)
+    assert len(per_label_metrics(counts, keep.tolist())) == K

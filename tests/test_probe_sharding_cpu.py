@@ -189,3 +189,38 @@ def test_metrics_from_confusion_counts_match_sklearn():
     m = metrics_from_counts(KIND_3CLASS, conf)
     assert abs(m["val_acc"] - float((p3 == t3).mean())) < 1e-12
     assert abs(m["val_f1"] - f1_score(t3, p3, labels=[0, 1, 2], average="macro", zero_division=0)) < 1e-12
+
+
+def test_per_label_metrics_match_sklearn():
+    """per_label_metrics (from integer counts) == the sklearn calls of eval_probes_per_label.py:77-96, including the
+    single-class NaN convention and the empty-mask skip."""
+    from sklearn.metrics import balanced_accuracy_score, matthews_corrcoef, precision_recall_fscore_support
+
+    from openvla_probe_b200.probes import per_label_metrics
+
+    rng = np.random.default_rng(3)
+    N, K = 400, 9
+    y = rng.integers(-1, 2, (N, K))
+    p = rng.integers(0, 2, (N, K))
+    y[:, 2] = -1                                  # empty mask -> skipped
+    y[:, 3] = np.where(y[:, 3] == 0, 1, y[:, 3])  # single class (all positives) -> mcc / bal_acc NaN
+    p[:, 4] = 0                                   # never predicted positive -> precision 0 by zero_division
+    counts = np.zeros((K, 4), dtype=np.int64)
+    for k in range(K):
+        m = y[:, k] != -1
+        t, q = (y[m, k] == 1), p[m, k] == 1
+        counts[k] = [(t & q).sum(), (~t & q).sum(), (t & ~q).sum(), (~t & ~q).sum()]
+    keep = list(range(10, 10 + K))
+    recs = per_label_metrics(counts, keep)
+    assert [r["label_idx"] for r in recs] == [10, 11, 13, 14, 15, 16, 17, 18]
+    for r in recs:
+        k = r["label_idx"] - 10
+        m = y[:, k] != -1
+        targ, pred = (y[m, k] == 1).astype(int), p[m, k]
+        pr, rc, f1, _ = precision_recall_fscore_support(targ, pred, average="binary", pos_label=1, zero_division=0)
+        assert abs(r["prec"] - pr) < 1e-12 and abs(r["recall"] - rc) < 1e-12 and abs(r["f1"] - f1) < 1e-12
+        if len(np.unique(targ)) > 1:
+            assert abs(r["mcc"] - matthews_corrcoef(targ, pred)) < 1e-12
+            assert abs(r["bal_acc"] - balanced_accuracy_score(targ, pred)) < 1e-12
+        else:
+            assert np.isnan(r["mcc"]) and np.isnan(r["bal_acc"])
