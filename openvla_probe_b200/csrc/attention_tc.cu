@@ -1,5 +1,5 @@
 // tcgen05 / TMEM flash attention: the causal Llama prefill (head_dim 128, K/V in the cache layout) and the
-// non-causal head_dim-64 ViT tower (q, k, v packed in one [B*T, 3D] buffer).
+// non-causal ViT towers (q, k, v packed in one [B*T, 3D] buffer): head_dim 64 (DINOv2) and 72 (SigLIP).
 //
 // A work item = 128 query rows of one (batch, head); keys are consumed in chunks of 64 with an online softmax.
 // CTAs are persistent (two per SM) and walk a static, cost-balanced list of items.
@@ -20,6 +20,10 @@
 // Tiles are aligned to the END of the sequence (the ragged tile is the first one, which under the causal mask has the
 // fewest keys), and the last chunk of a tile is shortened to a multiple of 16 keys.
 // head_dim 128: Q 32 KB + 3 K stages + 2 V stages of 16 KB = 112 KB and 256 TMEM columns: two CTAs per SM.
+// head_dim 72: every operand is a 128B-swizzled 64-column slab plus a 32B-swizzled 16-column slab (3-D tensor maps
+// zero-fill columns 72..79): QK^T takes a fifth K = 16 step from the tail slabs, PV a second N = 16 product.
+// A wait on a multi-phase mbarrier that some threads skip would alias phases: the end-of-item wait has its own
+// barrier (bar_done), and the optional rescale wait is argued safe where it is issued.
 #include <stdio.h>
 #include <stdlib.h>
 
