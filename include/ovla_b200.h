@@ -152,6 +152,8 @@ int ovla_bind_weight(OvlaEngine* e, const char* name, const void* src_dev, const
 int ovla_finalize(OvlaEngine* e);
 long long ovla_workspace_bytes(const OvlaEngine* e);
 long long ovla_weight_bytes(const OvlaEngine* e);
+/* number of passes ovla_run has replayed from a captured CUDA graph (small batches: first call eager, second captures) */
+long long ovla_graph_replays(const OvlaEngine* e);
 
 typedef struct OvlaRunArgs {
   const long long* input_ids_dev; /* int64 [B, P], first id = BOS; the host has already appended 29871 */

@@ -104,6 +104,7 @@ struct OvlaEngine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<GraphKey, GraphEntry> graphs;
+  long long graph_replays = 0;  // cudaGraphLaunch calls made by ovla_run (tests assert that a replay happened)
   // staging for ovla_run_host
   long long* in_ids = nullptr;
   bf16* in_px = nullptr;
@@ -292,6 +293,7 @@ extern "C" void ovla_destroy(OvlaEngine* e) {
 
 extern "C" long long ovla_workspace_bytes(const OvlaEngine* e) { return e ? e->workspace_bytes : 0; }
 extern "C" long long ovla_weight_bytes(const OvlaEngine* e) { return e ? e->weight_bytes : 0; }
+extern "C" long long ovla_graph_replays(const OvlaEngine* e) { return e ? e->graph_replays : 0; }
 
 // ----------------------------------------------------------------------------------------------- weight binding
 static long long numel(const long long* shape, int ndim) {
@@ -758,6 +760,7 @@ extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
   CUDA_TRY(cudaEventRecord(e->ev_in, user));
   CUDA_TRY(cudaStreamWaitEvent(e->own_stream, e->ev_in, 0));
   CUDA_TRY(cudaGraphLaunch(g.exec, e->own_stream));
+  ++e->graph_replays;
   CUDA_TRY(cudaEventRecord(e->ev_out, e->own_stream));
   CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
   count_launch(static_cast<int>(g.launches));

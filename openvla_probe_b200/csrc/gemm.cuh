@@ -59,6 +59,9 @@ struct GemmShape {
 #ifndef OVLA_EPI_SLOTS
 #define OVLA_EPI_SLOTS 1
 #endif
+#ifndef OVLA_RES_FENCE
+#define OVLA_RES_FENCE 1
+#endif
 static constexpr int kGemmThreads = 384;
 static constexpr int kEpiWarps = 8;
 static constexpr int kBM = 128;           // rows per CTA
@@ -276,6 +279,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int g = 0; g < 4; ++g) rr[g] = *reinterpret_cast<const uint4*>(sr + lane * 64 + ((g ^ sw) << 4));
             ++n_res;
+#if OVLA_RES_FENCE
+            fence_proxy_async();   // order this lane's generic-proxy reads before the async-proxy (TMA) refill
+#endif
             __syncwarp();          // every lane has read its row: the slot may be refilled
             fetch_res(c + 2 * SL);
           }
