@@ -139,17 +139,20 @@ def prepare_object(cache: Dict[int, dict]) -> ProbeSplit:
     return ProbeSplit(train_ids, val_ids, keep, pw, Y_full.shape[1])
 
 
-def prepare_spatial(cache: Dict[int, dict]) -> ProbeSplit:
-    """train_spatial_probes.py:100-131: labels are {0,1}; keep = columns with both values in the TRAIN split;
-    pos_weight = clamp(neg/pos, max=20) with pos_cnt = Y_train.sum(0) (Appendix B pitfall kept)."""
+def prepare_spatial(cache: Dict[int, dict], all_label_mats: Optional[Sequence[torch.Tensor]] = None) -> ProbeSplit:
+    """train_spatial_probes.py:96-131.  keep = columns that show both a 0 and a 1 over ALL episode files -- the script
+    stacks `all_files`, i.e. also the rollouts dropped by --exclude_eps (pass their label matrices as `all_label_mats`;
+    default: the cached episodes); pos_cnt = Y_train.sum(0) (labels assumed {0, 1}: the script does not mask -1, SURVEY
+    Appendix B), neg_cnt = N_train - pos_cnt, pos_weight = clamp((neg + 1) / (pos + 1), max=20)[keep]."""
     train_ids, val_ids = split_episodes(cache)
-    Y_tr = _stack_labels(cache, train_ids).float()
-    pos = Y_tr.sum(0)
-    neg = Y_tr.shape[0] - pos
-    keep = ((pos > 0) & (neg > 0)).nonzero(as_tuple=True)[0]
+    Y_full = torch.cat(list(all_label_mats), 0) if all_label_mats is not None else _stack_labels(cache, sorted(cache))
+    keep = ((Y_full == 1).any(0) & (Y_full == 0).any(0)).nonzero(as_tuple=True)[0]
     if len(keep) == 0:
-        raise RuntimeError("No label flips value across the training episodes.")
-    pw = (neg[keep] / pos[keep].clamp(min=1.0)).clamp(max=20)
+        raise RuntimeError("Even across all episodes no label flips value.")
+    Y_tr = _stack_labels(cache, train_ids)
+    pos = Y_tr.sum(0).float()
+    neg = Y_tr.shape[0] - pos
+    pw = ((neg + 1.0) / (pos + 1.0))[keep].clamp(max=20)
     return ProbeSplit(train_ids, val_ids, keep, pw, Y_tr.shape[1])
 
 
@@ -576,8 +579,12 @@ def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 2
     import pandas as pd
 
     cache = load_episodes(log_dir, exclude)
-    split = {KIND_OBJECT: prepare_object, KIND_SPATIAL: prepare_spatial, KIND_DUAL: prepare_dual,
-             KIND_3CLASS: prepare_3class}[kind](cache)
+    if kind == KIND_SPATIAL:      # the spatial script decides `keep` over every episode file, excluded ones too
+        every = cache if not exclude else load_episodes(log_dir, ())
+        split = prepare_spatial(cache, [torch.cat([every[i]["symbolic_state_object_relations"],
+                                                   every[i]["symbolic_state_action_subgoals"]], 1) for i in sorted(every)])
+    else:
+        split = {KIND_OBJECT: prepare_object, KIND_DUAL: prepare_dual, KIND_3CLASS: prepare_3class}[kind](cache)
     if kind in (KIND_DUAL, KIND_3CLASS):
         torch.manual_seed(seed)
     records = []

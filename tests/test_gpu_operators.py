@@ -251,6 +251,66 @@ def test_attention_tcgen05_many_waves_deterministic(L):
     assert int((err > 2.0 ** -7 * ref.abs().clamp_min(1.0)).sum()) == 0
 
 
+@pytest.mark.parametrize("hd,T,H,B", [(64, 261, 16, 40), (72, 256, 16, 40)])
+def test_vit_attention_tcgen05_many_waves_deterministic(L, hd, T, H, B):
+    """The two ViT shapes (DINOv2: head_dim 64, 261 tokens; SigLIP: head_dim 72, 256 tokens) with 640 (batch, head)
+    sequences = many waves of the persistent CTAs: three launches bit-identical and within 2 bf16 ulps of the oracle."""
+    _lib, lib = L
+    D = H * hd
+    g = torch.Generator().manual_seed(hd)
+    qkv = bf(torch.randn(B, T, 3, H, hd, generator=g))
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    ref = O._sdpa(q.float(), k.float(), v.float(), causal=False).permute(0, 2, 1, 3).reshape(B * T, D)
+    buf = qkv.reshape(B * T, 3 * D).contiguous().cuda()
+    outs = []
+    for _ in range(3):
+        out = torch.zeros(B * T, D, dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.ovla_attention_tc_qkv(P(buf), C.c_longlong(3 * D), P(out), C.c_longlong(D), B, H, T, hd, 0, None))
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    err = (outs[0].float() - ref).abs()
+    assert float(err.max()) <= 2 * 2.0 ** -8 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(1100, 4096, 4096), (1100, 4096, 11008), (1024, 1152, 4304), (20 * 261, 1024, 4096)])
+def test_gemm_inplace_residual_ragged_multi_tile_bit_exact(L, M, N, K):
+    """The engine always calls the residual epilogue IN PLACE (out == resid: o_proj / down_proj / ViT proj / fc2).  At
+    ragged M with more tiles than workers (M = 1100, N = 4096 as CTA pairs: 80 tile pairs on 74 workers, the second
+    CTA of the last pair fully out of bounds) a worker runs several tiles and its residual staging slot is refilled by
+    TMA while the previous chunk is still being read: round 1 ordered that refill with __syncwarp only and, rarely, a
+    lane read the NEXT chunk's residual (run-to-run differences of whole 16-byte pieces; found by
+    tools/determinism_bisect.py, fixed with a proxy fence).  Repeated in-place launches must equal the out-of-place
+    result bit for bit for the heuristic tile and for every forced tile shape, and must not write outside [0, M)."""
+    _lib, lib = L
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, generator=g, device="cuda") * 0.5)
+    W = bf(torch.randn(N, K, generator=g, device="cuda") * 0.03)
+    X = bf(torch.randn(M, N, generator=g, device="cuda"))
+
+    def call(out, resid, bn, cg):
+        epi = _lib.GemmEpilogue()
+        epi.resid_bf16, epi.ld_resid = resid.data_ptr(), N
+        _lib.check(lib.ovla_gemm(P(A), C.c_longlong(K), P(W), C.c_longlong(K), M, N, K, 0, 0, P(out), C.c_longlong(N),
+                                 C.byref(epi), bn, cg, None))
+
+    ref = torch.empty_like(X)
+    call(ref, X, 0, 0)
+    torch.cuda.synchronize()
+    want = (A.float() @ W.float().t()).bfloat16().float() + X.float()
+    ok, e = close_bf16(ref, want, ulps=3.0)
+    assert ok, e
+    for bn, cg in [(0, 0), (256, 2), (128, 1), (128, 2), (64, 1)]:
+        for rep in range(6):
+            buf = torch.full((M + 64, N), 7.0, dtype=torch.bfloat16, device="cuda")
+            buf[:M].copy_(X)
+            call(buf[:M], buf[:M], bn, cg)
+            torch.cuda.synchronize()
+            n_bad = int((buf[:M] != ref).sum())
+            assert n_bad == 0, (bn, cg, rep, n_bad)
+            assert bool((buf[M:] == 7.0).all()), (bn, cg, rep, "stored outside [0, M)")
+
+
 @pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])
 def test_decode_rope_attention_and_cache_append(L, B, ctx):
     """Fused RoPE + KV append + 1-query attention == oracle llama attention step with a KV cache."""
