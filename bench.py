@@ -46,6 +46,11 @@ def parse_args():
     ap.add_argument("--config", default="openvla-7b", choices=["openvla-7b", "siglip-7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bs1", action="store_true")
+    ap.add_argument("--no-probe", action="store_true", help="skip the probe-training leg (configs[3])")
+    ap.add_argument("--probe-only", action="store_true", help="run only the probe-training leg and print its block")
+    ap.add_argument("--probe-kind", default="object", choices=["object", "spatial", "dual"])
+    ap.add_argument("--probe-layers", type=int, default=33)
+    ap.add_argument("--probe-chunks", type=int, default=0)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--lite", action="store_true",
                     help="profiling mode for ncu: exactly --warmup untimed steps, no e2e / bs1 / CPU legs")
@@ -241,6 +246,91 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- probe-training leg
+def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str = "object", G: int = 33, batch: int = 4096,
+                       D: int = 4096, K: int = 439, steps: int = 12, warmup: int = 3, chunks: int = 0):
+    """BASELINE.json configs[3]: linear (object) probes of all 33 captured layers trained concurrently on synthetic
+    4096-d features, multilabel BCE, AdamW; at N > 1 every rank takes its own batch of 4096 rows per layer-step (weak
+    scaling, global batch 4096 x N) and the flat [dW | db | stats] gradients go through NCCL all-reduce, chunked and
+    overlapped with the next chunk's compute (probes.MultiLayerProbeTrainer).  Device-timed with CUDA events, max over
+    ranks.  Returns the `probe_training` block of the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+
+    from openvla_probe_b200.probes import MultiLayerProbeTrainer
+
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    n_ep = 2                                                   # steps per epoch held resident
+    N = batch * n_ep                                           # this rank's own rows
+    X = torch.randn(G, N, D, generator=g, device="cuda", dtype=torch.float32)
+    Y = (torch.rand(N, 481, generator=g, device="cuda") < 0.5).to(torch.int8)
+    Y[torch.rand(N, 481, generator=g, device="cuda") < 0.5] = -1
+    keep = torch.arange(K)
+    torch.manual_seed(0)
+    pw = torch.tensor(1.7) if kind == "dual" else torch.ones(K) * 2.0
+    tr = MultiLayerProbeTrainer(kind, G, D, K, pw, batch=batch, device=local, chunks=chunks, shard="local")
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(1))
+    tr.load_epoch(X, Y, keep, perm, drop_last=True)
+    del X
+    assert len(tr.steps) == n_ep
+    for s in range(max(3, warmup)):
+        tr.train_step(s % n_ep)
+    tr.finish()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    lib.ovla_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        tr.train_step(s % n_ep)
+    tr.finish()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = int(lib.ovla_launch_count())
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # all-reduce alone (same buffers, no compute beside it), for the record
+    ar_ms = None
+    if world > 1:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.all_reduce(tr.Gbuf)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            dist.all_reduce(tr.Gbuf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 3
+    losses = tr.step_losses()
+    ms_step = float(ms.item()) / steps
+    rows = tr.rows
+    # algorithmic HBM bytes of one layer-step (fp32): X_b read by the forward and again (transposed copy) by dW;
+    # W read; Z and dZ^T written and read once; labels; dW written; AdamW reads p, g, m, v and writes p, m, v
+    bytes_ls = 4.0 * (2 * batch * D + rows * D + 4 * batch * rows + rows * D + 7 * rows * D) + batch * tr.Kpad
+    flops_ls = 2 * 2.0 * batch * D * rows
+    us_ls = ms_step * 1e3 / G
+    out = {
+        "metric": "probe layer-steps/s (one AdamW step of one layer's probe on a batch of 4096 rows per GPU)",
+        "kind": kind, "value": world * G * 1e3 / ms_step, "unit": "layer-steps/s", "n_gpus": world, "scaling": "weak",
+        "layers_concurrent": G, "batch_per_gpu": batch, "global_batch": batch * world, "D": D, "K": K, "steps": steps,
+        "ms_per_step_all_layers": ms_step, "us_per_layer_step": us_ls, "samples_per_s": world * batch * G * 1e3 / ms_step,
+        "dtype": "tf32 GEMM (fp32 accumulate) / fp32 elsewhere", "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": bytes_ls / (us_ls * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": bytes_ls / (us_ls * 1e-6) / 1e9 / peaks["hbm_gbs"], "bytes_per_layer_step": bytes_ls,
+                     "tf32_tflops": flops_ls / (us_ls * 1e-6) / 1e12,
+                     "note": "whole layer-step (4 grouped launches), not a single kernel; the two TF32 GEMMs carry "
+                             f"{flops_ls / 1e9:.1f} GFLOP per layer-step"},
+        "allreduce": {"bytes_per_step": int(tr.Gbuf.numel() * 4) if world > 1 else 0, "chunks": len(tr.chunks),
+                      "alone_ms": ar_ms, "overlapped": world > 1 and len(tr.chunks) > 1,
+                      "sm_limit_of_gemms": tr.sm_limit},
+        "loss_layer0": losses[0],
+    }
+    del tr
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
@@ -265,6 +355,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
+
+    if args.probe_only:
+        blk = probe_training_leg(world, rank, local, lib, load_peaks(), kind=args.probe_kind, G=args.probe_layers,
+                                 steps=args.steps, warmup=args.warmup, chunks=args.probe_chunks)
+        if rank == 0:
+            print(json.dumps(blk), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     base = {"openvla-7b": cfgmod.openvla_7b, "siglip-7b": cfgmod.siglip_7b, "tiny": cfgmod.tiny}[args.config]()
     stats = {"synthetic": {"action": {"q01": np.linspace(-0.9, -0.3, 7).tolist(), "q99": np.linspace(0.4, 1.0, 7).tolist(),
@@ -292,9 +392,8 @@ def main():
     n_warm = args.warmup if args.lite else max(3, args.warmup)
     for _ in range(n_warm):
         step_device()
-    # ---- device-resident timing (value)
-    cat_n = (C.c_longlong * 7)(); cat_ms = (C.c_double * 7)(); cat_fl = (C.c_double * 7)(); cat_by = (C.c_double * 7)()
-    lib.ovla_profile_enable(1)
+    # ---- device-resident timing (value): per-kernel event profiler OFF (it costs two cudaEventRecord per launch)
+    lib.ovla_profile_enable(0)
     lib.ovla_reset_launch_count()
     sampler = ClockSampler(local)
     barrier()
@@ -308,13 +407,27 @@ def main():
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = int(lib.ovla_launch_count())
-    lib.ovla_profile_enable(0)
-    _lib.check(lib.ovla_profile_collect(cat_n, cat_ms, cat_fl, cat_by))
     t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * B / (ms_step / 1e3)
+
+    # ---- a SEPARATE profiled pass of the same steps: per-kernel CUDA events on the launch stream -> kernel_breakdown
+    # and the roofline of the dominant kernel family (its own step time is reported as profiled_ms_per_step)
+    cat_n = (C.c_longlong * 7)(); cat_ms = (C.c_double * 7)(); cat_fl = (C.c_double * 7)(); cat_by = (C.c_double * 7)()
+    prof_steps = args.steps if args.lite else max(1, min(args.steps, 3))
+    lib.ovla_profile_enable(1)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(prof_steps):
+        step_device()
+    p1.record()
+    barrier()
+    lib.ovla_profile_enable(0)
+    _lib.check(lib.ovla_profile_collect(cat_n, cat_ms, cat_fl, cat_by))
+    prof_ms_step = p0.elapsed_time(p1) / prof_steps
 
     # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region)
     if args.lite:
@@ -366,16 +479,28 @@ def main():
             lat_e2e.append((time.perf_counter() - t0) * 1e3)
         bs1 = {"p50_ms": statistics.median(lat), "e2e_p50_ms": statistics.median(lat_e2e)}
 
+    peaks = load_peaks()
+    # ---- probe training (configs[3]) on the same GPUs: all ranks take part (NCCL gradient all-reduce at N > 1)
+    probe_block = None
+    if not args.lite and not args.no_probe:
+        model.engine.close()
+        del model
+        torch.cuda.empty_cache()
+        try:
+            probe_block = probe_training_leg(world, rank, local, lib, peaks)
+        except Exception as ex:  # noqa: BLE001 -- recorded, never takes the headline number down
+            probe_block = {"error": f"{type(ex).__name__}: {ex}"}
+        model = None
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    peaks = load_peaks()
     traffic, traffic_note = ncu_traffic()
     names = ["gemm_tcgen05", "gemv", "flash_attn", "decode_attn", "norm", "pool", "other"]
-    cats = {n: {"launches": int(cat_n[i]), "ms_per_step": cat_ms[i] / args.steps,
+    cats = {n: {"launches": int(cat_n[i]), "ms_per_step": cat_ms[i] / prof_steps,
                 "tflops": (cat_fl[i] / (cat_ms[i] * 1e-3) / 1e12) if cat_ms[i] > 0 and cat_fl[i] > 0 else None,
                 "gbs": (cat_by[i] / (cat_ms[i] * 1e-3) / 1e9) if cat_ms[i] > 0 and cat_by[i] > 0 else None}
             for i, n in enumerate(names)}
@@ -385,7 +510,9 @@ def main():
         "kernel": "gemm_tcgen05_kernel (all ViT / projector / Llama linears of the step)",
         "bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["launches"] / args.steps,
+        "share_of_step": g["ms_per_step"] / prof_ms_step, "launches_per_step": g["launches"] / prof_steps,
+        "timing": f"CUDA events around every launch on its launch stream, in a separate pass of {prof_steps} step(s) right after "
+                  f"the timed region (value is timed with this profiler off); profiled step {prof_ms_step:.1f} ms",
         "traffic": traffic, "traffic_note": traffic_note,
         "decode_attn_hbm": {"achieved_gbs": cats["decode_attn"]["gbs"], "peak_gbs": peaks["hbm_gbs"],
                             "frac": (cats["decode_attn"]["gbs"] or 0.0) / peaks["hbm_gbs"]},
@@ -408,9 +535,12 @@ def main():
     }
     if bs1:
         line["bs1_latency"] = bs1
+    if probe_block:
+        line["probe_training"] = probe_block
     if world == 1 and not args.no_cpu_baseline:
-        model.engine.close()
-        del model
+        if model is not None:
+            model.engine.close()
+            del model
         torch.cuda.empty_cache()
         try:
             r = cpu_reference_run(args.config, P0, 1, 0, 90.0)

@@ -59,7 +59,15 @@ enum { OVLA_KIND_BF16 = 0, OVLA_KIND_TF32 = 1 };
 int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int N, int K, int mode,
               int kind, void* out_dev, long long ldo, const OvlaGemmEpilogue* epi, int tile_n, int cta_group,
               void* stream);
-
+/* `groups` independent fp32-output GEMMs of one shape in ONE persistent launch (the probes of all captured layers
+ * train concurrently: train_object_probes.py:208-232 loops over the layers one at a time):
+ *   out_g[M,N] = a_g[M,K] . w_g[N,K]^T (+ bias_f32_g),  operands of consecutive groups `*_gs` ELEMENTS apart.
+ * kind: OVLA_KIND_*; every base / pitch / group stride must be a multiple of 16 bytes.  sm_limit > 0 caps the number
+ * of SMs the persistent grid occupies (leave room for a collective running beside it), 0 = all SMs.            */
+int ovla_gemm_grouped(const void* a_dev, long long lda, long long a_gs, const void* w_dev, long long ldw, long long w_gs,
+                      int groups, int M, int N, int K, int kind, float* out_dev, long long ldo, long long out_gs,
+                      const float* bias_f32_dev, long long bias_gs, int tile_n, int cta_group, int sm_limit,
+                      void* stream);
 
 /* LayerNorm(eps, affine) over rows of a bf16 [rows, D] matrix (timm Block.norm1/norm2). */
 int ovla_layernorm(const void* x_dev, long long ldx, const void* w_dev, const void* b_dev, float eps, void* out_dev,
@@ -196,6 +204,18 @@ int ovla_probe_gather_labels(const signed char* y_dev, long long ldy, const long
 int ovla_probe_bce_grad(const float* z_dev, long long ldz, const signed char* yp_dev, int n, int K, int Kpad,
                         int kind0, int heads, const float* pos_weight_dev, float pos_weight_scalar, float* dzt_dev,
                         long long ldt, float* stats_dev, void* stream);
+/* The same loss / gradient for `groups` probes that share the labels (one probe per captured layer), fused with the
+ * bias gradient and the loss statistics, all deterministic (no floating-point atomics): z [groups][n][ldz] (z_gs
+ * apart), dzt [groups][heads*Kpad][ldt] (dzt_gs apart); for group g the bias gradient goes to
+ * out_base + g*out_gs + db_off [heads*Kpad] and {loss_h0, count_h0, loss_h1, count_h1} to out_base + g*out_gs +
+ * stats_off (overwritten, not accumulated) -- i.e. straight into the flat [dW | db | stats] gradient buffer that is
+ * all-reduced.  part_dev: groups * isplits * (heads*Kpad + 4*ceil(Kpad/32)) floats of scratch; ticket_dev: `groups`
+ * ints, zero on entry (left zero); isplits (1..64) CTAs share the batch of one (group, label tile).             */
+int ovla_probe_bce_grad_grouped(const float* z_dev, long long ldz, long long z_gs, const signed char* yp_dev, int n,
+                                int K, int Kpad, int kind0, int heads, const float* pos_weight_dev,
+                                float pos_weight_scalar, float* dzt_dev, long long ldt, long long dzt_gs, int groups,
+                                float* out_base_dev, long long out_gs, long long db_off, long long stats_off,
+                                float* part_dev, int isplits, int* ticket_dev, void* stream);
 /* Direct 3-class probe (train_3class_direct.py:147-212): z fp32 [n, 3K] viewed as [n*K, 3], class-weighted CE over
  * {-1 -> 0, 0 -> 1, 1 -> 2}; UN-normalised gradient transposed into dzt [rows_pad >= 3K, n]; stats[0] += sum w*nll,
  * stats[1] += sum w (the weighted-mean normaliser).  class_w3_host: 3 floats on the HOST.                      */
@@ -220,6 +240,13 @@ int ovla_probe_rowsum(const float* a_dev, long long lda, int rows, int cols, flo
 int ovla_probe_adamw(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, long long n_w, int D,
                      int rows_per_head, long long n_total, const float* stats_dev, float lr, float beta1, float beta2,
                      float eps, float wd, int step, void* stream);
+
+/* AdamW for `groups` probes in one launch: parameters / moments [groups][n_total] contiguous, gradients g_gs apart and
+ * statistics stats_gs apart (both inside the flat all-reduced buffer).                                          */
+int ovla_probe_adamw_grouped(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, int groups, long long n_w,
+                             int D, int rows_per_head, long long n_total, long long g_gs, const float* stats_dev,
+                             long long stats_gs, float lr, float beta1, float beta2, float eps, float wd, int step,
+                             void* stream);
 
 #ifdef __cplusplus
 }

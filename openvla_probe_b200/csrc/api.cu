@@ -63,10 +63,23 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
     e.gelu = epi->gelu;
     e.round_bf16 = epi->round_bf16;
   }
-  return gemm_launch(a_dev, lda, w_dev, ldw, M, N, K, mode, kind, e, tile_n, cta_group, num_sms(),
-                     static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // do not create a workspace for shapes that never split (gemm.cu)
+  const SplitKWs ws = (tile_n <= 0 && splitk_eligible(M, N, kind)) ? splitk_stream_workspace(st) : SplitKWs{nullptr, 0};
+  return gemm_launch(a_dev, lda, w_dev, ldw, M, N, K, mode, kind, e, tile_n, cta_group, num_sms(), st, ws);
 }
 
+
+int ovla_gemm_grouped(const void* a_dev, long long lda, long long a_gs, const void* w_dev, long long ldw, long long w_gs,
+                      int groups, int M, int N, int K, int kind, float* out_dev, long long ldo, long long out_gs,
+                      const float* bias_f32_dev, long long bias_gs, int tile_n, int cta_group, int sm_limit,
+                      void* stream) {
+  if (!a_dev || !w_dev || !out_dev) return set_error("ovla_gemm_grouped: null buffer");
+  int sms = num_sms();
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit < 2 ? 2 : sm_limit;
+  return gemm_grouped_launch(a_dev, lda, a_gs, w_dev, ldw, w_gs, groups, M, N, K, kind, out_dev, ldo, out_gs,
+                             bias_f32_dev, bias_gs, tile_n, cta_group, sms, static_cast<cudaStream_t>(stream));
+}
 
 int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K, int T,
                        int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev, long long ldo,
@@ -185,6 +198,22 @@ int ovla_probe_adamw(float* p, const float* g, float* m, float* v, long long n_w
                      int step, void* stream) {
   return probe_adamw_launch(p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, step,
                             static_cast<cudaStream_t>(stream));
+}
+
+int ovla_probe_bce_grad_grouped(const float* z, long long ldz, long long z_gs, const signed char* y, int n, int K,
+                                int Kpad, int kind0, int heads, const float* pos_weight, float pos_weight_scalar,
+                                float* dzt, long long ldt, long long dzt_gs, int groups, float* out_base, long long out_gs,
+                                long long db_off, long long stats_off, float* part, int isplits, int* ticket,
+                                void* stream) {
+  return probe_bce_grad_grouped_launch(z, ldz, z_gs, y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar, dzt, ldt,
+                                       dzt_gs, groups, out_base, out_gs, db_off, stats_off, part, isplits, ticket,
+                                       static_cast<cudaStream_t>(stream));
+}
+int ovla_probe_adamw_grouped(float* p, const float* g, float* m, float* v, int groups, long long n_w, int D,
+                             int rows_per_head, long long n_total, long long g_gs, const float* stats, long long stats_gs,
+                             float lr, float beta1, float beta2, float eps, float wd, int step, void* stream) {
+  return probe_adamw_launch(p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, step,
+                            static_cast<cudaStream_t>(stream), groups, g_gs, stats_gs);
 }
 
 }  // extern "C"

@@ -91,6 +91,8 @@ struct OvlaEngine {
   float *pooled = nullptr, *logits = nullptr;
   long long* tokens = nullptr;
   int* err_flag = nullptr;
+  // split-K partial-tile scratch, one per stream this engine issues GEMMs on (never shared with another engine)
+  SplitKWs ws_main = {nullptr, 0}, ws_side = {nullptr, 0};
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
@@ -256,6 +258,17 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   W(&e->logits, B * d.vocab);
   W(&e->tokens, 64LL * B);
   W(&e->err_flag, 4);
+  {
+    // split-K runs only for M <= 512 rows (gemm.cu): S <= 8 slices of [M, N] fp32; sized for the widest such GEMM
+    // (the vocabulary / gate_up for the LLM stream, the tower MLP for the side stream), capped at 192 MB
+    const long long n_main = std::max<long long>(2LL * d.llm_inter, d.vocab);
+    e->ws_main.floats = std::min<long long>(48LL << 20, 8LL * 512 * n_main);
+    W(&e->ws_main.ptr, e->ws_main.floats);
+    if (d.n_towers == 2) {
+      e->ws_side.floats = std::min<long long>(48LL << 20, 8LL * 512 * std::max<long long>(maxMlp, 3 * maxD));
+      W(&e->ws_side.ptr, e->ws_side.floats);
+    }
+  }
   e->max_P = static_cast<int>(T - e->np);
   W(&e->in_ids, B * std::max(1, e->max_P));
   W(&e->in_px, B * 3LL * d.n_towers * d.image_size * d.image_size);
@@ -463,7 +476,7 @@ extern "C" int ovla_finalize(OvlaEngine* e) {
 namespace {
 
 // out = A . W^T with epilogue; picks the weight-streaming kernel for M <= 8
-int linear(const bf16* A, long long lda, const Slot& W, int M, int mode, void* out, long long ldo, const bf16* bias,
+int linear(OvlaEngine* e, const bf16* A, long long lda, const Slot& W, int M, int mode, void* out, long long ldo, const bf16* bias,
            const bf16* scale, const bf16* resid, long long ldr, int gelu, int round_bf16, cudaStream_t st) {
   GemmEpi epi = {};
   epi.out = out;
@@ -476,7 +489,9 @@ int linear(const bf16* A, long long lda, const Slot& W, int M, int mode, void* o
   epi.round_bf16 = round_bf16;
   const int N = static_cast<int>(W.rows), K = static_cast<int>(W.cols);
   if (M <= 8) return gemv_launch(A, lda, W.ptr, K, M, N, K, mode, epi, st);
-  return gemm_launch(A, lda, W.ptr, K, M, N, K, mode, kKindBf16, epi, 0, 0, num_sms(), st);
+  // split-K partial tiles go to the workspace of the stream the GEMM runs on (the two towers overlap in time)
+  const SplitKWs ws = (e->side_stream && st == e->side_stream) ? e->ws_side : e->ws_main;
+  return gemm_launch(A, lda, W.ptr, K, M, N, K, mode, kKindBf16, epi, 0, 0, num_sms(), st, ws);
 }
 
 int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::VitBufs& v, cudaStream_t st) {
@@ -487,7 +502,7 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::Vit
   const int rows = B * N;
   // patch embed: im2col -> GEMM(+bias) -> (+pos_embed, prefix tokens)
   OVLA_TRY(im2col_launch(px, B, 3 * d.n_towers, 3 * t, d.image_size, d.image_size, d.patch, e->kpad, v.im2col, st));
-  OVLA_TRY(linear(v.im2col, e->kpad, tw.patch_w, B * np, kModeBf16, v.patch, D, tw.patch_b.ptr, nullptr, nullptr,
+  OVLA_TRY(linear(e, v.im2col, e->kpad, tw.patch_w, B * np, kModeBf16, v.patch, D, tw.patch_b.ptr, nullptr, nullptr,
                   0, 0, 0, st));
   OVLA_TRY(assemble_tokens_launch(v.patch, tw.pos.ptr, tw.cls.ptr, tw.reg.ptr, B, np, w.n_prefix, D, v.x, st));
   const long long s12[12] = {3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd, 3LL * D * N, 3LL * D, hd,
@@ -495,16 +510,16 @@ int run_tower(OvlaEngine* e, int t, const bf16* px, int B, const OvlaEngine::Vit
   for (int i = 0; i < e->n_run[t]; ++i) {
     BlockW& b = tw.blocks[i];
     OVLA_TRY(layernorm_launch(v.x, D, b.ln1_w.ptr, b.ln1_b.ptr, 1e-6f, v.h, D, rows, D, st));
-    OVLA_TRY(linear(v.h, D, b.qkv_w, rows, kModeBf16, v.qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(linear(e, v.h, D, b.qkv_w, rows, kModeBf16, v.qkv, 3LL * D, b.qkv_b.ptr, nullptr, nullptr, 0, 0, 0, st));
     if (e->attn_tc && (hd == 64 || hd == 72))
       OVLA_TRY(attn_tc_qkv_launch(v.qkv, 3LL * D, v.attn, D, B, w.heads, N, hd, 0, st));
     else
       OVLA_TRY(flash_attn_launch(v.qkv, v.qkv + D, v.qkv + 2 * D, v.attn, s12, B, w.heads, N, N, hd, 0, st));
     // x = x + ls1(proj(attn))   (in place: each epilogue thread reads its residual before writing)
-    OVLA_TRY(linear(v.attn, D, b.proj_w, rows, kModeBf16, v.x, D, b.proj_b.ptr, b.ls1.ptr, v.x, D, 0, 0, st));
+    OVLA_TRY(linear(e, v.attn, D, b.proj_w, rows, kModeBf16, v.x, D, b.proj_b.ptr, b.ls1.ptr, v.x, D, 0, 0, st));
     OVLA_TRY(layernorm_launch(v.x, D, b.ln2_w.ptr, b.ln2_b.ptr, 1e-6f, v.h, D, rows, D, st));
-    OVLA_TRY(linear(v.h, D, b.fc1_w, rows, kModeBf16, v.mlp, w.mlp, b.fc1_b.ptr, nullptr, nullptr, 0, 1, 0, st));
-    OVLA_TRY(linear(v.mlp, w.mlp, b.fc2_w, rows, kModeBf16, v.x, D, b.fc2_b.ptr, b.ls2.ptr, v.x, D, 0, 0, st));
+    OVLA_TRY(linear(e, v.h, D, b.fc1_w, rows, kModeBf16, v.mlp, w.mlp, b.fc1_b.ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e, v.mlp, w.mlp, b.fc2_w, rows, kModeBf16, v.x, D, b.fc2_b.ptr, b.ls2.ptr, v.x, D, 0, 0, st));
   }
   // strip prefix tokens, concat on the feature dim (modeling_prismatic.py:123)
   int col0 = 0;
@@ -559,7 +574,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       epi.H = H;
       OVLA_TRY(gemm_launch(e->l_h, D, l.qkv_w.ptr, D, rows, 3 * D, D, kModeQkvRope, kKindBf16, epi, 0, 0, num_sms(), st));
     } else {
-      OVLA_TRY(linear(e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
+      OVLA_TRY(linear(e, e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
       OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
                               Tmax, st));
     }
@@ -567,11 +582,11 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       OVLA_TRY(attn_tc_prefill_launch(e->l_qkv, 3LL * D, e->k_cache(i), e->v_cache(i), e->l_attn, D, B, H, T, Tmax, st));
     else
       OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
-    OVLA_TRY(linear(e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(linear(e, e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));
-    OVLA_TRY(linear(e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,
+    OVLA_TRY(linear(e, e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,
                     0, st));
-    OVLA_TRY(linear(e->l_act, d.llm_inter, l.down_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(linear(e, e->l_act, d.llm_inter, l.down_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
   }
   // final norm (hidden_states[L] is post-norm)
   OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, rows, D, st));
@@ -596,17 +611,17 @@ int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t s
   for (int i = 0; i < d.llm_layers; ++i) {
     LayerW& l = e->layers[i];
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, B, D, st));
-    OVLA_TRY(linear(e->l_h, D, l.qkv_w, B, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(linear(e, e->l_h, D, l.qkv_w, B, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
     OVLA_TRY(decode_rope_attn_launch(e->l_qkv, 3LL * D, e->rope_cos.ptr, e->rope_sin.ptr, pos, e->k_cache(i),
                                      e->v_cache(i), B, H, hd, Tmax, e->l_attn, D, st));
-    OVLA_TRY(linear(e->l_attn, D, l.o_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(linear(e, e->l_attn, D, l.o_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, B, D, st));
-    OVLA_TRY(linear(e->l_h, D, l.gate_up_w, B, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0, 0,
+    OVLA_TRY(linear(e, e->l_h, D, l.gate_up_w, B, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0, 0,
                     st));
-    OVLA_TRY(linear(e->l_act, d.llm_inter, l.down_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
+    OVLA_TRY(linear(e, e->l_act, d.llm_inter, l.down_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
   }
   OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, B, D, st));
-  OVLA_TRY(linear(e->l_h, D, e->lm_head, B, kModeF32, logits, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
+  OVLA_TRY(linear(e, e->l_h, D, e->lm_head, B, kModeF32, logits, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
   return 0;
 }
 
@@ -641,10 +656,7 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     CUDA_TRY(cudaEventRecord(e->ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
     OVLA_TRY(run_tower(e, 0, px, B, e->vb[0], st));
-    set_splitk_slot(1);   // the towers overlap in time: the side stream's split-K GEMMs get their own partial-tile buffer
-    const int rc_side = run_tower(e, 1, px, B, e->vb[1], e->side_stream);
-    set_splitk_slot(0);
-    if (rc_side) return rc_side;
+    OVLA_TRY(run_tower(e, 1, px, B, e->vb[1], e->side_stream));
     CUDA_TRY(cudaEventRecord(e->ev_join, e->side_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
   } else {
@@ -655,13 +667,13 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     CUDA_TRY(cudaMemcpyAsync(a->patches_out_dev, e->p_cat, sizeof(bf16) * Mp * Dv, cudaMemcpyDeviceToDevice, st));
   const bf16* proj_out;
   if (e->n_proj == 3) {
-    OVLA_TRY(linear(e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, 4LL * Dv, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
-    OVLA_TRY(linear(e->p_1, 4LL * Dv, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 1, 0, st));
-    OVLA_TRY(linear(e->p_2, D, e->pj_w[2], Mp, kModeBf16, e->p_3, D, e->pj_b[2].ptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(linear(e, e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, 4LL * Dv, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e, e->p_1, 4LL * Dv, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e, e->p_2, D, e->pj_w[2], Mp, kModeBf16, e->p_3, D, e->pj_b[2].ptr, nullptr, nullptr, 0, 0, 0, st));
     proj_out = e->p_3;
   } else {
-    OVLA_TRY(linear(e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, D, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
-    OVLA_TRY(linear(e->p_1, D, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 0, 0, st));
+    OVLA_TRY(linear(e, e->p_cat, Dv, e->pj_w[0], Mp, kModeBf16, e->p_1, D, e->pj_b[0].ptr, nullptr, nullptr, 0, 1, 0, st));
+    OVLA_TRY(linear(e, e->p_1, D, e->pj_w[1], Mp, kModeBf16, e->p_2, D, e->pj_b[1].ptr, nullptr, nullptr, 0, 0, 0, st));
     proj_out = e->p_2;
   }
   if (a->projector_out_dev)
@@ -679,7 +691,7 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     float* lg = a->step_logits_out_dev ? a->step_logits_out_dev + 1LL * s * B * d.vocab : e->logits;
     if (s == 0) {
       // HF: logits = lm_head(h) in bf16, then .float()  => fp32 storage of bf16-rounded values
-      OVLA_TRY(linear(e->l_h + 1LL * (T - 1) * D, 1LL * T * D, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr,
+      OVLA_TRY(linear(e, e->l_h + 1LL * (T - 1) * D, 1LL * T * D, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr,
                       nullptr, 0, 0, 1, st));
     } else {
       OVLA_TRY(embed_splice_launch(e->tokens + 1LL * (s - 1) * B, B, 1, e->embed.ptr, d.vocab, nullptr, 0, D, e->l_x,

@@ -82,7 +82,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     attr_set = true;
   }
   const int tile_m = kBM * CG;
-  const int tiles = ((s.M + tile_m - 1) / tile_m) * ((s.N + BN - 1) / BN) * s.split_k;
+  const int tiles = ((s.M + tile_m - 1) / tile_m) * ((s.N + BN - 1) / BN) * s.split_k * (s.groups > 1 ? s.groups : 1);
   int workers = num_sms / CG;
   if (workers > tiles) workers = tiles;
   cudaLaunchConfig_t cfg = {};
@@ -97,7 +97,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(kCatGemm, 2.0 * s.M * s.N * s.K, 0.0, stream);
+  ProfScope prof(kCatGemm, 2.0 * s.M * s.N * s.K * (s.groups > 1 ? s.groups : 1), 0.0, stream);
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, s, e));
   count_launch();
   return 0;
@@ -114,9 +114,73 @@ static int dispatch_tile(int bn, int cg, const CUtensorMap& ta, const CUtensorMa
   return set_error("gemm: unsupported tile config bn=%d cg=%d", bn, cg);
 }
 
+// Shapes that may be split along K (the caller then has to pass a workspace): the small-M weight-streaming bf16
+// GEMMs (bs=1 prefill, batched decode) and the single-probe TF32 GEMMs (64 tiles on 148 SMs without a split).
+bool splitk_eligible(int M, int N, int kind) {
+  return kind == kKindBf16 ? M <= 512 : 1LL * M * N <= (4LL << 20);
+}
+
+// 3-D view (k, row, group) of `groups` equally shaped row-major [rows, cols] matrices `group_stride` elements apart;
+// box = [1 group, box_rows, 128 bytes]: rows beyond `rows` read as zeros instead of running into the next group
+static int make_tmap_3d_groups(CUtensorMap* m, const void* ptr, int elem_bytes, long long rows, long long cols,
+                               long long ld, long long group_stride, int groups, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15) || ((group_stride * elem_bytes) & 15))
+    return set_error("grouped TMA operand must be 16-byte aligned with 16-byte multiple row / group pitches");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * elem_bytes, static_cast<cuuint64_t>(group_stride) * elem_bytes};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (grouped) failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+// `groups` independent fp32-output GEMMs of one shape in a single persistent launch (probe training over all captured
+// layers at once: 33 x 64 tiles fill the 148 SMs that a single probe's 64 tiles cannot):
+//   out_g[M, N] = A_g[M, K] . W_g[N, K]^T (+ bias_g),  g < groups,  operands `*_gs` elements apart.
+int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void* W, long long ldw, long long w_gs,
+                        int groups, int M, int N, int K, int kind, float* out, long long ldo, long long out_gs,
+                        const float* bias_f32, long long bias_gs, int bn, int cg, int num_sms, cudaStream_t stream) {
+  if (groups <= 0 || M <= 0 || N <= 0 || K <= 0) return set_error("grouped gemm: empty shape G=%d M=%d N=%d K=%d", groups, M, N, K);
+  if (N % 4) return set_error("grouped gemm: N=%d must be a multiple of 4", N);
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || ((ldo * 4) & 15) || ((out_gs * 4) & 15))
+    return set_error("grouped gemm: output must be 16-byte aligned with 16-byte multiple pitches");
+  if (groups == 1) {   // plain 2-D path
+    GemmEpi e1 = {};
+    e1.out = out;
+    e1.ldo = ldo;
+    e1.bias_f32 = bias_f32;
+    return gemm_launch(A, lda, W, ldw, M, N, K, kModeF32, kind, e1, bn, cg, num_sms, stream);
+  }
+  const int eb = kind == kKindBf16 ? 2 : 4;
+  if (bn <= 0) {
+    const long long m128 = (M + 127) / 128, m256 = (M + 255) / 256;
+    if (groups * m256 * ((N + 255LL) / 256) * 2 >= num_sms) { bn = 256; cg = 2; }
+    else if (groups * m128 * ((N + 127LL) / 128) >= num_sms) { bn = 128; cg = 1; }
+    else { bn = 64; cg = 1; }
+  }
+  CUtensorMap ta, tb;
+  if (make_tmap_3d_groups(&ta, A, eb, M, K, lda, a_gs, groups, kBM)) return -1;
+  if (make_tmap_3d_groups(&tb, W, eb, N, K, ldw, w_gs, groups, bn / cg)) return -1;
+  const int num_k = (K + (128 / eb) - 1) / (128 / eb);
+  GemmShape s{M, N, K, 16, 1, num_k, kL2EvictNormal, kL2EvictNormal, groups};
+  GemmEpi e = {};
+  e.out = out;
+  e.ldo = ldo;
+  e.bias_f32 = bias_f32;
+  e.out_gs = out_gs;
+  e.bias_gs = bias_gs;
+  if (kind == kKindBf16) return dispatch_tile<kModeF32, kKindBf16>(bn, cg, ta, tb, ta, ta, s, e, num_sms, stream);
+  return dispatch_tile<kModeF32, kKindTf32>(bn, cg, ta, tb, ta, ta, s, e, num_sms, stream);
+}
+
 // Public (library-internal) entry. A: [M,K] lda; W: [N,K] ldw. kind: 0 bf16, 1 tf32(fp32 storage).
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
-                const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream) {
+                const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream, SplitKWs ws) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm: empty shape M=%d N=%d K=%d", M, N, K);
   const int eb = kind == kKindBf16 ? 2 : 4;
   if (mode == kModeBf16 && (N % 8)) return set_error("gemm: N=%d must be a multiple of 8", N);
@@ -167,9 +231,9 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   // split-K for the small-M weight-streaming shapes (see splitk.cu)
   const int num_k = (K + (128 / eb) - 1) / (128 / eb);
   int split = 1;
-  if (auto_tile && g_split != 0 && g_split != 1 && M <= 512 && kind == kKindBf16 &&
-      (mode == kModeBf16 || mode == kModeSwiGLU || mode == kModeF32) && (mode == kModeSwiGLU ? (N / 2) % 8 == 0 : N % 8 == 0)) {
-    if (N < 8192) { bn = 128; cg = 1; }
+  if (auto_tile && g_split != 0 && g_split != 1 && splitk_eligible(M, N, kind) &&
+      (kind == kKindBf16 ? (mode == kModeBf16 || mode == kModeSwiGLU || mode == kModeF32) : mode == kModeF32) && (mode == kModeSwiGLU ? (N / 2) % 8 == 0 : N % 8 == 0)) {
+    if (kind == kKindBf16 && N < 8192) { bn = 128; cg = 1; }
     const long long tiles_mn = ((M + 128LL * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
     // pick the slice count that minimises (waves of CTAs) x (K blocks per slice) + the reduce kernel (fixed cost +
     // its fp32 workspace traffic at ~2 MB per unit), in units of one K block (~0.35 us); split only long-K problems
@@ -189,8 +253,8 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
       if (best * 100 > base * 85) want = 1;
     }
     want = std::min(want, 8);
-    while (want >= 2 && 1LL * want * M * N > splitk_workspace_floats()) --want;
-    if (want >= 2 && splitk_workspace()) {
+    while (want >= 2 && 1LL * want * M * N > ws.floats) --want;
+    if (want >= 2 && ws.ptr) {
       const int kps = (num_k + want - 1) / want;
       split = (num_k + kps - 1) / kps;
     }
@@ -202,11 +266,12 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     const int kps = (num_k + split - 1) / split;
     GemmShape s{M, N, K, group, split, kps, l2_a, l2_b};
     GemmEpi pe = {};
-    pe.out = splitk_workspace();
+    pe.out = ws.ptr;
     pe.ldo = N;
     pe.ldr = 1LL * M * N;  // slice stride
-    OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, ta, ta, s, pe, num_sms, stream)));
-    return splitk_epilogue_launch(mode, splitk_workspace(), 1LL * M * N, N, split, M, N, epi, stream);
+    if (kind == kKindBf16) OVLA_TRY((dispatch_tile<kModePartial, kKindBf16>(bn, cg, ta, tb, ta, ta, s, pe, num_sms, stream)));
+    else OVLA_TRY((dispatch_tile<kModePartial, kKindTf32>(bn, cg, ta, tb, ta, ta, s, pe, num_sms, stream)));
+    return splitk_epilogue_launch(mode, ws.ptr, 1LL * M * N, N, split, M, N, epi, stream);
   }
   GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b};
   if (kind == kKindBf16 && (mode == kModeBf16 || mode == kModeSwiGLU)) {

@@ -46,6 +46,8 @@ struct GemmEpi {
   __nv_bfloat16* v_cache;
   int T, pos0, Tmax, H;
   int tma_epi;  // kModeBf16: output (and residual) tiles move through shared memory with TMA (tensor maps passed beside)
+  // grouped GEMM (GemmShape::groups > 1, kModeF32 only): element strides between the groups' outputs / fp32 biases
+  long long out_gs, bias_gs;
 };
 
 struct GemmShape {
@@ -54,6 +56,9 @@ struct GemmShape {
   int split_k;  // K slices (each tile of a slice accumulates kb_per_split K blocks); 1 = no split
   int kb_per_split;
   unsigned long long l2_a, l2_b;  // L2 eviction-priority hints of the A / W tile loads (kL2Evict*)
+  // > 1: `groups` independent problems of the same shape in one launch (the probes of all captured layers): A and W
+  // are 3-D tensor maps (k, row, group) whose row boxes clip at the group's own M / N, tiles are numbered group-major
+  int groups;
 };
 
 #ifndef OVLA_EPI_SLOTS
@@ -123,7 +128,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_m = (shape.M + kTileM - 1) / kTileM;
   const int num_n = (shape.N + BN - 1) / BN;
   const int tiles_mn = num_m * num_n;
-  const int num_tiles = tiles_mn * shape.split_k;
+  const int n_groups = shape.groups > 1 ? shape.groups : 1;
+  const int num_tiles = tiles_mn * shape.split_k * n_groups;
   const int num_k = (shape.K + kKElems - 1) / kKElems;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
@@ -160,8 +166,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int t = worker; t < num_tiles; t += num_workers) {
         int mb, nb;
-        const int slice = t / tiles_mn;
-        gemm_tile_coords(t - slice * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
+        const int outer = t / tiles_mn;
+        const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
+        gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
         const int row_a = mb * kTileM + static_cast<int>(cta_rank) * kBM;
         const int row_b = nb * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
@@ -169,7 +176,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
-          if constexpr (CG == 1) {
+          if (shape.groups > 1) {
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_3d(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a, gidx);
+              tma_load_3d(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, gidx);
+            } else {
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              tma_load_3d_pair(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a, gidx);
+              tma_load_3d_pair(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, gidx);
+            }
+          } else if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d_hint(&tmap_a, &full_bar[stage], sa, kb * kKElems, row_a, shape.l2_a);
             tma_load_2d_hint(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, shape.l2_b);
@@ -194,7 +211,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const int slice = t / tiles_mn;
+        const int slice = (t / tiles_mn) % shape.split_k;
         const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -227,8 +244,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t n_req = 0;
     for (int t = worker; t < num_tiles; t += num_workers) {
       int mb, nb;
-      const int slice = t / tiles_mn;
-      gemm_tile_coords(t - slice * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
+      const int outer = t / tiles_mn;
+      const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
+      gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
@@ -586,7 +604,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       } else {  // kModeF32
-        float* out = reinterpret_cast<float*>(epi.out) + static_cast<long long>(row) * epi.ldo;
+        float* out = reinterpret_cast<float*>(epi.out) + gidx * epi.out_gs + static_cast<long long>(row) * epi.ldo;
+        const float* bias_f32 = epi.bias_f32 ? epi.bias_f32 + gidx * epi.bias_gs : nullptr;
 #pragma unroll 1
         for (int c = part; c < BN / 32; c += 2) {
           uint32_t v[32];
@@ -602,7 +621,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               x[i] = __uint_as_float(v[g * 4 + i]);
-              if (epi.bias_f32) x[i] += epi.bias_f32[cg + i];
+              if (bias_f32) x[i] += bias_f32[cg + i];
               if (epi.bias) x[i] += __bfloat162float(epi.bias[cg + i]);
               if (epi.round_bf16) x[i] = bf16_round(x[i]);
             }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void dot_row(const __nv_bfloat16* __restrict__ w, uin
 }
 
 template <int MB, int MODE, int kCh>
-__global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(256) ovla_wstream_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                             const __nv_bfloat16* __restrict__ W, long long ldw, int M,
                                                             int N, int K, GemmEpi epi) {
   const int lane = threadIdx.x & 31;
@@ -164,7 +164,7 @@ static int gemv_launch_t(const __nv_bfloat16* X, long long ldx, const __nv_bfloa
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
   cfg.numAttrs = (use_pdl() && pdl_enabled()) ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemv_kernel<MB, MODE, kCh>, X, ldx, Wp, ldw, M, N, K, epi));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, ovla_wstream_kernel<MB, MODE, kCh>, X, ldx, Wp, ldw, M, N, K, epi));
   count_launch();
   return 0;
 }

@@ -11,12 +11,20 @@ namespace ovla {
 int num_sms();
 
 // gemm.cu -- tcgen05 GEMM
+// `ws`: caller-owned fp32 scratch for split-K partial tiles (one per stream that may run GEMMs concurrently); an empty
+// workspace disables split-K
+struct SplitKWs {
+  float* ptr;
+  long long floats;
+};
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
-                const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream);
-// splitk.cu -- split-K workspace + reduce/epilogue
-float* splitk_workspace();
-void set_splitk_slot(int slot);  // workspace used by the GEMMs issued next from this thread (0 main stream, 1 side stream)
-long long splitk_workspace_floats();
+                const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream, SplitKWs ws = SplitKWs{nullptr, 0});
+bool splitk_eligible(int M, int N, int kind);
+int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void* W, long long ldw, long long w_gs,
+                        int groups, int M, int N, int K, int kind, float* out, long long ldo, long long out_gs,
+                        const float* bias_f32, long long bias_gs, int bn, int cg, int num_sms, cudaStream_t stream);
+// splitk.cu -- reduce/epilogue of the split-K partial tiles; workspace of the engine-less ovla_gemm entry
+SplitKWs splitk_stream_workspace(cudaStream_t st);
 int splitk_epilogue_launch(int mode, const float* ws, long long slice_stride, long long ldw, int S, int M, int N,
                            const GemmEpi& epi, cudaStream_t st);
 // gemv.cu -- M <= 8 weight streaming
@@ -77,7 +85,12 @@ int probe_bce_grad_launch(const float* Z, long long ldz, const signed char* Y, i
 int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float* out, cudaStream_t st);
 int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
                        long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
-                       int step, cudaStream_t st);
+                       int step, cudaStream_t st, int groups = 1, long long g_gs = 0, long long stats_gs = 0);
+int probe_bce_grad_grouped_launch(const float* Z, long long ldz, long long z_gs, const signed char* Y, int n, int K,
+                                  int Kpad, int kind0, int heads, const float* pos_weight, float pos_weight_scalar,
+                                  float* dZT, long long ldt, long long dzt_gs, int groups, float* out_base,
+                                  long long out_gs, long long db_off, long long stats_off, float* part, int isplits,
+                                  int* ticket, cudaStream_t st);
 
 // probe3.cu
 int probe_ce3_grad_launch(const float* Z, long long ldz, const signed char* Y, long long ldy, int n, int K,

@@ -166,6 +166,174 @@ int probe_bce_grad_launch(const float* Z, long long ldz, const signed char* Y, i
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------- grouped, fused step
+// The same loss / gradient for `groups` probes at once (one per captured layer: same labels, different logits), with
+// the bias gradient (row sums of dZ^T) and the loss statistics produced by the same kernel, DETERMINISTICALLY:
+// grid = (k-tiles of 32 labels, i-splits, groups); a CTA walks its share of the batch in [128 x 32] tiles, keeps
+// per-label column sums and the four loss statistics in registers, and writes them as partials; the last CTA of a
+// group to finish (ticket counter) adds the partials in a fixed order into db[groups][rows] and stats[groups][4].
+// Nothing is accumulated with floating-point atomics, so a step is bit-reproducible.
+//   Z    [groups][n][ldz]  (z_gs apart)      dZT [groups][heads*Kpad][ldt]  (dzt_gs apart)
+//   db   = out_base + g*out_gs + db_off      stats = out_base + g*out_gs + stats_off   (the flat [dW | db | stats] buffer)
+//   part [groups][isplits][heads*Kpad + 4*ktiles] floats, ticket [groups] ints (zero on entry, left zero)
+__global__ void __launch_bounds__(256) bce_grad_grouped_kernel(const float* __restrict__ Z, long long ldz, long long z_gs,
+                                                               const signed char* __restrict__ Y, int n, int K, int Kpad,
+                                                               int kind0, int heads, const float* __restrict__ pos_weight,
+                                                               float pos_weight_scalar, float* __restrict__ dZT,
+                                                               long long ldt, long long dzt_gs, float* __restrict__ out_base,
+                                                               long long out_gs, long long db_off, long long stats_off,
+                                                               float* __restrict__ part, int* __restrict__ ticket) {
+  constexpr int TI = 128;
+  __shared__ float tile[2][TI][33];
+  __shared__ float red[8][8][32];   // [value: db0, db1, stats 0..3 -> rows 2..5][warp][lane]
+  __shared__ int s_last;
+  const int ktiles = gridDim.x, isplits = gridDim.y, grp = blockIdx.z;
+  const int k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rows = heads * Kpad;
+  Z += grp * z_gs;
+  dZT += grp * dzt_gs;
+  const int n_it = (n + TI - 1) / TI;
+  const int it0 = static_cast<int>(1LL * n_it * blockIdx.y / isplits), it1 = static_cast<int>(1LL * n_it * (blockIdx.y + 1) / isplits);
+  const int k = k0 + tx;
+  const bool k_ok = k < K;
+  const float pw = (kind0 == 2) ? pos_weight_scalar : (k_ok ? pos_weight[k] : 1.f);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float db0 = 0.f, db1 = 0.f;
+  for (int it = it0; it < it1; ++it) {
+    const int i0 = it * TI;
+    // all loads of the tile first (16 independent rows per thread), then the math
+    int yv[16];
+    float z0[16], z1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = i0 + ty + 8 * j;
+      const bool ok = k_ok && i < n;
+      yv[j] = ok ? Y[static_cast<long long>(i) * Kpad + k] : -2;
+      z0[j] = ok ? Z[static_cast<long long>(i) * ldz + k] : 0.f;
+      z1[j] = (ok && heads == 2) ? Z[static_cast<long long>(i) * ldz + Kpad + k] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float g0 = 0.f, g1 = 0.f;
+      const int y = yv[j];
+      if (y != -2) {
+        {
+          const float z = z0[j];
+          float t, valid;
+          if (kind0 == 0) { t = (y == 1); valid = (y != -1); }
+          else if (kind0 == 1) { t = static_cast<float>(y); valid = 1.f; }
+          else { t = (y != -1); valid = 1.f; }
+          const float lw = 1.f + (pw - 1.f) * t;
+          const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);
+          const float sig = 1.f / (1.f + expf(-z));
+          acc[0] += valid * ((1.f - t) * z + lw * sp);
+          acc[1] += valid;
+          g0 = valid * (sig * lw - pw * t);
+        }
+        if (heads == 2) {
+          const float z = z1[j];
+          const float t = (y == 1), valid = (y != -1);
+          const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);
+          const float sig = 1.f / (1.f + expf(-z));
+          acc[2] += valid * ((1.f - t) * z + sp);
+          acc[3] += valid;
+          g1 = valid * (sig - t);
+        }
+      }
+      db0 += g0;
+      db1 += g1;
+      tile[0][ty + 8 * j][tx] = g0;
+      if (heads == 2) tile[1][ty + 8 * j][tx] = g1;
+    }
+    __syncthreads();
+    // transposed store: label row k0 + r, 128 consecutive samples (4 lanes-of-32 segments per row)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int idx = threadIdx.x + 256 * j;    // 32 label rows x 128 samples
+      const int r = idx >> 7, c = idx & 127;
+      const int kk = k0 + r, i = i0 + c;
+      if (kk < Kpad && i < n) {
+        dZT[static_cast<long long>(kk) * ldt + i] = tile[0][c][r];
+        if (heads == 2) dZT[static_cast<long long>(Kpad + kk) * ldt + i] = tile[1][c][r];
+      }
+    }
+    __syncthreads();
+  }
+  // per-CTA partials, fixed order: db over the 8 row groups (warps), stats over lanes then warps
+  red[0][ty][tx] = db0;
+  red[1][ty][tx] = db1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0) red[2 + j][ty][0] = v;
+  }
+  __syncthreads();
+  float* my = part + (static_cast<long long>(grp) * isplits + blockIdx.y) * (rows + 4 * ktiles);
+  if (threadIdx.x < 64) {
+    const int h = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (h < heads && k0 + l < Kpad) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[h][w][l];
+      my[h * Kpad + k0 + l] = sum;
+    }
+  } else if (threadIdx.x < 68) {
+    const int j = threadIdx.x - 64;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[2 + j][w][0];
+    my[rows + 4 * blockIdx.x + j] = sum;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = ktiles * isplits;
+    s_last = (atomicAdd(ticket + grp, 1) == total - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* gp = part + static_cast<long long>(grp) * isplits * (rows + 4 * ktiles);
+  float* db = out_base + grp * out_gs + db_off;
+  float* stats = out_base + grp * out_gs + stats_off;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    float sum = 0.f;
+    for (int sidx = 0; sidx < isplits; ++sidx) sum += __ldcg(gp + static_cast<long long>(sidx) * (rows + 4 * ktiles) + r);
+    db[r] = sum;
+  }
+  if (threadIdx.x < 4) {
+    float sum = 0.f;
+    for (int sidx = 0; sidx < isplits; ++sidx)
+      for (int kt = 0; kt < ktiles; ++kt)
+        sum += __ldcg(gp + static_cast<long long>(sidx) * (rows + 4 * ktiles) + rows + 4 * kt + threadIdx.x);
+    stats[threadIdx.x] = sum;
+  }
+  if (threadIdx.x == 0) ticket[grp] = 0;
+}
+
+int probe_bce_grad_grouped_launch(const float* Z, long long ldz, long long z_gs, const signed char* Y, int n, int K,
+                                  int Kpad, int kind0, int heads, const float* pos_weight, float pos_weight_scalar,
+                                  float* dZT, long long ldt, long long dzt_gs, int groups, float* out_base,
+                                  long long out_gs, long long db_off, long long stats_off, float* part, int isplits,
+                                  int* ticket, cudaStream_t st) {
+  if (n <= 0 || groups <= 0) return 0;
+  if (heads != 1 && heads != 2) return set_error("probe: heads must be 1 or 2");
+  if (kind0 < 0 || kind0 > 2) return set_error("probe: unknown loss kind %d", kind0);
+  if (kind0 != 2 && !pos_weight) return set_error("probe: vector pos_weight required");
+  if (isplits < 1 || isplits > 64) return set_error("probe: isplits %d out of range [1, 64]", isplits);
+  if (!part || !ticket || !out_base) return set_error("probe: null workspace");
+  dim3 grid((Kpad + 31) / 32, isplits, groups);
+  ProfScope prof(kCatOther, 0.0, (8.0 * heads + 1.0) * n * Kpad * groups, st);
+  bce_grad_grouped_kernel<<<grid, 256, 0, st>>>(Z, ldz, z_gs, Y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar,
+                                                dZT, ldt, dzt_gs, out_base, out_gs, db_off, stats_off, part, ticket);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // db[r] = sum_i dZT[r, i]  (one warp per row)
 __global__ void rowsum_kernel(const float* __restrict__ A, long long lda, int rows, int cols, float* __restrict__ out) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -190,13 +358,17 @@ int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float
 // torch.optim.AdamW (decoupled weight decay), one thread per parameter.  params = [W (rows x D) | b (rows)] in one
 // flat buffer, grads likewise (un-normalised); row r of head h is divided by stats[2h+1], the global number of
 // loss terms of that head -- read from device memory, so no host sync separates loss and update.
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+// Grouped form: `groups` probes with parameters n_total apart and gradients / statistics g_gs / stats_gs apart.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g_all, float* __restrict__ m,
                              float* __restrict__ v, long long n_w, int D, int rows_per_head, long long n_total,
-                             const float* __restrict__ stats, float lr, float beta1, float beta2, float eps, float wd,
-                             float bc1, float bc2_sqrt) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_total) return;
-  const long long row = (i < n_w) ? i / D : i - n_w;
+                             const float* __restrict__ stats_all, float lr, float beta1, float beta2, float eps, float wd,
+                             float bc1, float bc2_sqrt, int groups, long long g_gs, long long stats_gs) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_total * groups) return;
+  const long long grp = i / n_total, j = i - grp * n_total;
+  const float* g = g_all + grp * g_gs - grp * n_total;   // so that g[i] below addresses this group's gradient j
+  const float* stats = stats_all + grp * stats_gs;
+  const long long row = (j < n_w) ? j / D : j - n_w;
   const int head = static_cast<int>(row / rows_per_head);
   const float denom = stats[2 * head + 1];  // global count of the head's loss terms (after the allreduce)
   const float grad = denom > 0.f ? g[i] / denom : 0.f;
@@ -211,15 +383,15 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 
 int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
                        long long n_total, const float* stats, float lr, float beta1, float beta2, float eps, float wd,
-                       int step, cudaStream_t st) {
-  if (n_total <= 0) return 0;
+                       int step, cudaStream_t st, int groups, long long g_gs, long long stats_gs) {
+  if (n_total <= 0 || groups <= 0) return 0;
   if (step < 1) return set_error("adamw: step must be >= 1");
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  ProfScope prof(kCatOther, 0.0, 28.0 * n_total, st);
-  adamw_kernel<<<static_cast<unsigned>((n_total + 255) / 256), 256, 0, st>>>(p, g, m, v, n_w, D, rows_per_head, n_total,
-                                                                             stats, lr, beta1, beta2, eps, wd, bc1,
-                                                                             static_cast<float>(sqrt(bc2)));
+  ProfScope prof(kCatOther, 0.0, 28.0 * n_total * groups, st);
+  adamw_kernel<<<static_cast<unsigned>((n_total * groups + 255) / 256), 256, 0, st>>>(
+      p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, bc1, static_cast<float>(sqrt(bc2)),
+      groups, g_gs, stats_gs);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;

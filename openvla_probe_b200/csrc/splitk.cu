@@ -1,38 +1,53 @@
 // Split-K for the weight-streaming GEMM shapes (M <= 512: bs=1 prefill, batched decode steps).
 // With few output tiles a plain tiling leaves most SMs idle and each active CTA limited by its own shared-memory
 // fill rate (~100 GB/s per SM); slicing K gives every SM a (tile, K-slice) pair.  Each slice writes its raw fp32
-// partial tile (kModePartial) into a fixed workspace [S, M, N]; this kernel sums the S partials IN SLICE ORDER
+// partial tile (kModePartial) into a workspace [S, M, N]; this kernel sums the S partials IN SLICE ORDER
 // (deterministic) and applies the same epilogue / rounding points as the fused GEMM epilogue.
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
 
+#include <map>
+#include <mutex>
+
 namespace ovla {
 
-static constexpr long long kSplitWsFloats = 48LL << 20;  // 192 MB, allocated once (never re-allocated: CUDA graphs keep the pointer)
-static constexpr int kSplitSlots = 2;                    // one workspace per concurrently running stream of an engine
-static float* g_split_ws[16][kSplitSlots] = {};
-static thread_local int g_split_slot = 0;
+// Workspaces are OWNED BY THE CALLER of gemm_launch (SplitKWs): an OvlaEngine allocates one per stream it issues GEMMs
+// on at ovla_create time (engine.cu), so two engines -- or two host threads -- on one device never share partial tiles
+// and nothing is allocated under stream capture.  The stand-alone ovla_gemm entry has no engine: it uses one lazily
+// allocated buffer per (device, stream), created outside capture only (a capturing stream without a buffer simply does
+// not split).
+static constexpr long long kStandaloneWsFloats = 48LL << 20;  // 192 MB
 
-// GEMMs issued between set_splitk_slot(s) calls use workspace s.  The engine runs its two vision towers on two
-// streams at small batch: their split-K GEMMs overlap in time (always under CUDA-graph replay), so each stream needs
-// its own partial-tile buffer.
-void set_splitk_slot(int slot) { g_split_slot = (slot >= 0 && slot < kSplitSlots) ? slot : 0; }
+namespace {
+struct WsKey {
+  int dev;
+  cudaStream_t st;
+  bool operator<(const WsKey& o) const { return dev != o.dev ? dev < o.dev : st < o.st; }
+};
+std::mutex g_ws_mu;
+std::map<WsKey, float*> g_ws;
+}  // namespace
 
-float* splitk_workspace() {
+SplitKWs splitk_stream_workspace(cudaStream_t st) {
   int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 16) return nullptr;
-  float*& ws = g_split_ws[dev][g_split_slot];
-  if (!ws) {
-    if (cudaMalloc(&ws, kSplitWsFloats * sizeof(float)) != cudaSuccess) {
-      cudaGetLastError();
-      ws = nullptr;
-    }
+  if (cudaGetDevice(&dev) != cudaSuccess) return {nullptr, 0};
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_ws.find(WsKey{dev, st});
+  if (it != g_ws.end()) return {it->second, kStandaloneWsFloats};
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return {nullptr, 0};
   }
-  return ws;
+  float* p = nullptr;
+  if (cudaMalloc(&p, kStandaloneWsFloats * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    return {nullptr, 0};
+  }
+  g_ws[WsKey{dev, st}] = p;
+  return {p, kStandaloneWsFloats};
 }
-long long splitk_workspace_floats() { return kSplitWsFloats; }
 
 // one thread = one row x 8 consecutive OUTPUT columns
 template <int MODE>

@@ -430,6 +430,257 @@ class ProbeTrainer:
                 on_epoch(e)
 
 
+class MultiLayerProbeTrainer:
+    """The probes of `G` captured layers trained CONCURRENTLY on the same shuffled batches (the reference loops over the
+    layers one at a time: train_object_probes.py:208-232; every layer sees the same labels, only the features differ).
+
+    One optimisation step of all G probes is four grouped launches (object / spatial / dual kinds):
+
+        logits_g = X_g W_g^T + b_g     one persistent tcgen05 TF32 GEMM over G x tiles        ovla_gemm_grouped
+        dZ^T_g, db_g, loss/count_g     fused BCE gradient + bias gradient + statistics,       ovla_probe_bce_grad_grouped
+                                       deterministic (no floating-point atomics)
+        dW_g = dZ^T_g X_g              grouped TF32 GEMM straight into the flat gradient      ovla_gemm_grouped
+        AdamW of all G probes          one launch                                             ovla_probe_adamw_grouped
+
+    A single probe has only 64 output tiles for 148 SMs; G x 64 tiles fill the machine.
+
+    Multi-GPU: the flat gradient buffer [G][dW | db | stats] is cut into `chunks` layer ranges; the all-reduce of chunk c
+    (NCCL, its own stream) runs while chunk c+1 computes, and AdamW of chunk c is issued one chunk later, so the
+    collective is hidden behind compute instead of trailing every step.  With world > 1 the persistent GEMMs leave
+    `comm_sms` SMs to the collective (a persistent grid that cannot get all its CTAs resident runs a second wave).
+    Parameters / moments / gradients of layer g live at [g] of P / M / V / G (so `trainer(g)`-style views are free)."""
+
+    def __init__(self, kind: str, G: int, D: int, K: int, pos_weight: torch.Tensor, batch: int = 4096, lr: float = 1e-3,
+                 weight_decay: float = 1e-4, device: int = 0, group=None, init_states: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
+                 chunks: int = 0, comm_sms: int = 16, shard: str = "split"):
+        from . import _lib
+
+        if kind not in _KIND0:
+            raise ValueError(f"grouped training covers object / spatial / dual probes, not {kind!r}")
+        self._lib_mod, self.lib = _lib, _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.OvlaError("probe training needs a CUDA device (sm_100a); there is no CPU fallback")
+        if D % 4:
+            raise ValueError("feature dim must be a multiple of 4")
+        import torch.distributed as dist
+
+        self.kind, self.G, self.D, self.K = kind, G, D, K
+        self.heads = 2 if kind == KIND_DUAL else 1
+        self.Kpad = (K + 7) // 8 * 8
+        self.n_out = K
+        self.rows_per_head = self.Kpad
+        self.rows = self.heads * self.Kpad
+        self.batch, self.lr, self.wd = batch, lr, weight_decay
+        self.dev = torch.device("cuda", device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        # "split": every global batch of `batch` rows is cut over the ranks (the reference's trajectory at any N);
+        # "whole": rank r takes global batches r, r + world, ... whole (global batch = world x batch);
+        # "local": X / Y handed to load_epoch are already this rank's own rows (global batch = world x batch)
+        if shard not in ("split", "whole", "local"):
+            raise ValueError(f"unknown shard mode {shard!r}")
+        self.shard = shard
+        self.n_w = self.rows * D
+        self.n_total = self.n_w + self.rows
+        self.gs = self.n_total + 4                # floats between the layers' [dW | db | stats] blocks (16-byte multiple)
+        self.P = torch.zeros(G, self.n_total, dtype=torch.float32, device=self.dev)
+        self.M = torch.zeros_like(self.P)
+        self.V = torch.zeros_like(self.P)
+        self.Gbuf = torch.zeros(G, self.gs, dtype=torch.float32, device=self.dev)
+        self.step_count = 0
+        if kind == KIND_DUAL:
+            self.pw_vec, self.pw_scalar = None, float(pos_weight)
+        else:
+            pw = torch.ones(self.Kpad, dtype=torch.float32)
+            pw[:K] = pos_weight.float()
+            self.pw_vec, self.pw_scalar = pw.to(self.dev), 1.0
+        if chunks <= 0:
+            chunks = 1 if self.world == 1 else min(G, 3)
+        chunks = max(1, min(chunks, G))
+        cuts = [round(i * G / chunks) for i in range(chunks + 1)]
+        self.chunks = [(cuts[i], cuts[i + 1]) for i in range(chunks) if cuts[i + 1] > cuts[i]]
+        self.sm_limit = 0
+        if self.world > 1 and comm_sms > 0:
+            n_sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            self.sm_limit = max(2, (n_sm - comm_sms) // 2 * 2)
+        self.isplits = 8
+        self.ktiles = (self.Kpad + 31) // 32
+        self.part = torch.zeros(G * self.isplits * (self.rows + 4 * self.ktiles), dtype=torch.float32, device=self.dev)
+        self.ticket = torch.zeros(G, dtype=torch.int32, device=self.dev)
+        self._pending = None                      # (chunk, all-reduce work handle) whose AdamW has not been issued yet
+        for g in range(G):
+            self._init_params(g, init_states[g] if init_states is not None else None)
+
+    def _init_params(self, g: int, init_state):
+        """nn.Linear default init drawn on the host in layer order (as the per-layer loop of the reference would)."""
+        W = self.P[g, : self.n_w].view(self.rows, self.D)
+        b = self.P[g, self.n_w:]
+        names = ["presence_head", "truth_head"] if self.heads == 2 else [None]
+        for h, nm in enumerate(names):
+            if init_state is None:
+                lin = torch.nn.Linear(self.D, self.K)
+                w0, b0 = lin.weight.detach(), lin.bias.detach()
+            else:
+                pre = f"{nm}." if nm else ""
+                w0, b0 = init_state[pre + "weight"].float(), init_state[pre + "bias"].float()
+            W[h * self.Kpad: h * self.Kpad + self.K].copy_(w0)
+            b[h * self.Kpad: h * self.Kpad + self.K].copy_(b0)
+
+    def state_dict(self, g: int) -> Dict[str, torch.Tensor]:
+        W = self.P[g, : self.n_w].view(self.rows, self.D)
+        b = self.P[g, self.n_w:]
+        if self.heads == 1:
+            return {"weight": W[: self.K].cpu().clone(), "bias": b[: self.K].cpu().clone()}
+        return {"presence_head.weight": W[: self.K].cpu().clone(), "presence_head.bias": b[: self.K].cpu().clone(),
+                "truth_head.weight": W[self.Kpad: self.Kpad + self.K].cpu().clone(),
+                "truth_head.bias": b[self.Kpad: self.Kpad + self.K].cpu().clone()}
+
+    # -- native calls --------------------------------------------------------------------------------
+    def _grouped_gemm(self, A, lda, a_gs, W, ldw, w_gs, groups, M, N, K, out, ldo, out_gs, bias=0, bias_gs=0):
+        self._lib_mod.check(self.lib.ovla_gemm_grouped(A, lda, a_gs, W, ldw, w_gs, groups, M, N, K, 1, out, ldo, out_gs,
+                                                       bias or None, bias_gs, 0, 0, self.sm_limit, self._lib_mod.stream_ptr()))
+
+    def logits(self, X: torch.Tensor) -> torch.Tensor:
+        """X fp32 [G, n, D] on the device -> logits fp32 [G, n, rows]."""
+        G, n = X.shape[0], X.shape[1]
+        assert G == self.G and X.is_contiguous()
+        Z = torch.empty(G, n, self.rows, dtype=torch.float32, device=self.dev)
+        if n:
+            self._grouped_gemm(X.data_ptr(), self.D, n * self.D, self.P.data_ptr(), self.D, self.n_total, G, n, self.rows,
+                               self.D, Z.data_ptr(), self.rows, n * self.rows, self.P.data_ptr() + self.n_w * 4, self.n_total)
+        return Z
+
+    def load_epoch(self, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, perm: torch.Tensor, drop_last: bool):
+        """X fp32 [G, N, D] (device), Y int8 [N, n_labels]: gather this rank's rows of the shuffled epoch into row-major
+        and transposed copies; every step starts at a row offset that is a multiple of 4 (16-byte aligned TMA bases)."""
+        n = X.shape[1]
+        if self.shard == "split":
+            ranges = shard_batches(n, self.batch, self.world, self.rank, drop_last)
+        elif self.shard == "local":
+            ranges = shard_batches(n, self.batch, 1, 0, drop_last)
+        else:
+            full = shard_batches(n, self.batch, 1, 0, drop_last)
+            n_steps = len(full) // self.world
+            ranges = [full[s * self.world + self.rank] for s in range(n_steps)]
+        pieces, self.steps, off = [], [], 0
+        for a, b in ranges:
+            m = b - a
+            pad = (-m) % 4
+            pieces.append(perm[a:b])
+            if pad:
+                pieces.append(perm[:1].expand(pad))
+            self.steps.append((off, off + m))
+            off += m + pad
+        idx = torch.cat(pieces) if pieces else perm[:0]
+        n_loc = idx.numel()
+        self.n_alloc = max(n_loc, 4)
+        self.Xp = torch.empty(self.G, self.n_alloc, self.D, dtype=torch.float32, device=self.dev)
+        self.XpT = torch.zeros(self.G, self.D, self.n_alloc, dtype=torch.float32, device=self.dev)
+        self.Yp = torch.empty(self.n_alloc, self.Kpad, dtype=torch.int8, device=self.dev)
+        idx_d = idx.to(self.dev, torch.int64)
+        keep_d = keep.to(self.dev, torch.int32)
+        st, ck = self._lib_mod.stream_ptr(), self._lib_mod.check
+        if n_loc:
+            for g in range(self.G):
+                ck(self.lib.ovla_probe_gather(X[g].data_ptr(), X.stride(1), idx_d.data_ptr(), n_loc, self.D,
+                                              self.Xp[g].data_ptr(), self.D, self.XpT[g].data_ptr(), self.n_alloc, st))
+            ck(self.lib.ovla_probe_gather_labels(Y.data_ptr(), Y.stride(0), idx_d.data_ptr(), keep_d.data_ptr(), n_loc,
+                                                 self.K, self.Kpad, self.Yp.data_ptr(), st))
+        bmax = max([hi - lo for lo, hi in self.steps], default=0)
+        self.bmax = max(bmax, 1)
+        self.ldz_t = max((bmax + 3) // 4 * 4, 4)
+        self.Z = torch.empty(self.G, self.bmax, self.rows, dtype=torch.float32, device=self.dev)
+        self.dZT = torch.zeros(self.G, self.rows, self.ldz_t, dtype=torch.float32, device=self.dev)
+
+    def _compute_chunk(self, g0: int, g1: int, lo: int, n: int) -> None:
+        ng = g1 - g0
+        f4 = 4
+        if n <= 0:
+            self.Gbuf[g0:g1].zero_()
+            return
+        P0 = self.P.data_ptr() + g0 * self.n_total * f4
+        Z0 = self.Z.data_ptr() + g0 * self.bmax * self.rows * f4
+        T0 = self.dZT.data_ptr() + g0 * self.rows * self.ldz_t * f4
+        G0 = self.Gbuf.data_ptr() + g0 * self.gs * f4
+        self._grouped_gemm(self.Xp.data_ptr() + (g0 * self.n_alloc + lo) * self.D * f4, self.D, self.n_alloc * self.D,
+                           P0, self.D, self.n_total, ng, n, self.rows, self.D, Z0, self.rows, self.bmax * self.rows,
+                           P0 + self.n_w * f4, self.n_total)
+        self._lib_mod.check(self.lib.ovla_probe_bce_grad_grouped(
+            Z0, self.rows, self.bmax * self.rows, self.Yp.data_ptr() + lo * self.Kpad, n, self.K, self.Kpad,
+            _KIND0[self.kind], self.heads, self.pw_vec.data_ptr() if self.pw_vec is not None else None, self.pw_scalar,
+            T0, self.ldz_t, self.rows * self.ldz_t, ng, G0, self.gs, self.n_w, self.n_total,
+            self.part.data_ptr() + g0 * self.isplits * (self.rows + 4 * self.ktiles) * f4, self.isplits,
+            self.ticket.data_ptr() + g0 * 4, self._lib_mod.stream_ptr()))
+        # dW_g[rows, D] = dZT_g[rows, n] . (XpT_g[:, lo:lo+n])^T
+        self._grouped_gemm(T0, self.ldz_t, self.rows * self.ldz_t,
+                           self.XpT.data_ptr() + (g0 * self.D * self.n_alloc + lo) * f4, self.n_alloc, self.D * self.n_alloc,
+                           ng, self.rows, self.D, n, G0, self.D, self.gs)
+
+    def _adamw_chunk(self, g0: int, g1: int, step: int) -> None:
+        f4 = 4
+        off = g0 * self.n_total * f4
+        G0 = self.Gbuf.data_ptr() + g0 * self.gs * f4
+        self._lib_mod.check(self.lib.ovla_probe_adamw_grouped(
+            self.P.data_ptr() + off, G0, self.M.data_ptr() + off, self.V.data_ptr() + off, g1 - g0, self.n_w, self.D,
+            self.rows_per_head, self.n_total, self.gs, G0 + self.n_total * f4, self.gs, self.lr, 0.9, 0.999, 1e-8, self.wd,
+            step, self._lib_mod.stream_ptr()))
+
+    def _flush_pending(self) -> None:
+        if self._pending is not None:
+            (g0, g1), work, step = self._pending
+            if work is not None:
+                work.wait()                       # the compute stream waits for the collective, not the host
+            self._adamw_chunk(g0, g1, step)
+            self._pending = None
+
+    def train_step(self, s: int) -> None:
+        """One optimisation step of all G probes on local rows self.steps[s] (all ranks in lock-step)."""
+        import torch.distributed as dist
+
+        lo, hi = self.steps[s]
+        self.step_count += 1
+        for (g0, g1) in self.chunks:
+            self._compute_chunk(g0, g1, lo, hi - lo)
+            work = None
+            if self.world > 1:
+                work = dist.all_reduce(self.Gbuf[g0:g1], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._flush_pending()                 # AdamW of the PREVIOUS chunk, whose all-reduce ran beside this compute
+            self._pending = ((g0, g1), work, self.step_count)
+            if len(self.chunks) == 1:
+                self._flush_pending()             # a single chunk has nothing to hide behind
+
+    def finish(self) -> None:
+        """Issue the AdamW update still in flight (call before reading parameters or statistics)."""
+        self._flush_pending()
+
+    def step_losses(self) -> List[float]:
+        """Loss of the last step for every layer (host sync)."""
+        self.finish()
+        st = self.Gbuf[:, self.n_total:].cpu()
+        out = []
+        for g in range(self.G):
+            loss = float(st[g, 0] / st[g, 1]) if st[g, 1] > 0 else 0.0
+            if self.heads == 2 and st[g, 3] > 0:
+                loss += float(st[g, 2] / st[g, 3])
+            out.append(loss)
+        return out
+
+    def fit(self, X: torch.Tensor, Y: torch.Tensor, keep: torch.Tensor, epochs: int, seed: int = 0,
+            drop_last: bool = False, on_epoch: Optional[Callable[[int], None]] = None) -> None:
+        X = X.to(self.dev, torch.float32).contiguous()
+        Y = Y.to(self.dev, torch.int8).contiguous()
+        g = torch.Generator().manual_seed(seed)
+        for e in range(epochs):
+            perm = torch.randperm(X.shape[1], generator=g)
+            self.load_epoch(X, Y, keep, perm, drop_last)
+            for s in range(len(self.steps)):
+                self.train_step(s)
+            self.finish()
+            if on_epoch:
+                on_epoch(e)
+
+
 # ----------------------------------------------------------------------------------------------- evaluation (host, as reference)
 def _f1_binary_macro(tp: int, fp: int, fn: int, tn: int) -> float:
     """sklearn.metrics.f1_score(y_true, y_pred, average="macro", zero_division=0) from the confusion counts: per-class F1
@@ -529,6 +780,15 @@ def evaluate(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.Tensor,
         # accuracy / F1 from integer confusion counts computed next to the logits: only 9 integers leave the GPU.
         # Average precision needs the sorted scores and stays on the sklearn path (on_device=False).
         Z = trainer.logits(X.to(trainer.dev, torch.float32).contiguous())
+        if kind == KIND_SPATIAL:
+            # train_spatial_probes.py:165-176 hands sklearn the 2-D indicator matrices: "macro" then averages the
+            # positive-class F1 of every label column (not the two classes of the flattened problem)
+            c = per_label_counts(trainer, Z, Y, keep, thresh).astype(np.int64)
+            tp, fp, fn, tn = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+            den = 2 * tp + fp + fn
+            f1 = np.where(den > 0, 2.0 * tp / np.maximum(den, 1), 0.0)
+            n = int(c.sum())
+            return dict(val_acc=float((tp + tn).sum() / n) if n else 0.0, val_f1=float(f1.mean()) if len(f1) else 0.0)
         return metrics_from_counts(kind, confusion_counts(kind, trainer, Z, Y, keep, thresh))
     return _evaluate_host(kind, trainer, X, Y, keep, thresh)
 
@@ -558,10 +818,15 @@ def _evaluate_host(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.T
                             zero_division=0) if mask.any() else 0.0
         return dict(pres_acc_va=pres_acc, truth_acc_va=truth_acc, pres_f1_va=pres_f1, truth_f1_va=truth_f1)
     probs = Z[:, :K].sigmoid()
-    if kind == KIND_OBJECT:
-        mask, target = (y != -1), (y == 1).float()
-    else:
-        mask, target = torch.ones_like(y, dtype=torch.bool), y.float()
+    if kind == KIND_SPATIAL:                      # train_spatial_probes.py:165-176: no mask, 2-D multilabel sklearn inputs
+        target = y.float()
+        pred = (probs > thresh).float()
+        if not y.numel():
+            return dict(val_acc=0.0, val_f1=0.0, val_ap=0.0)
+        return dict(val_acc=float((pred == target).float().mean()),
+                    val_f1=f1_score(target.numpy(), pred.numpy(), average="macro", zero_division=0),
+                    val_ap=average_precision_score(target.numpy(), probs.numpy(), average="macro"))
+    mask, target = (y != -1), (y == 1).float()
     if not mask.any():
         return dict(val_acc=0.0, val_f1=0.0, val_ap=0.0)
     pred = (probs > thresh).long()

@@ -31,6 +31,28 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.ovla_abi_version() == 1
 
 
+def test_every_entry_point_has_header_derived_argtypes(lib):
+    """no call may rely on the call site wrapping 64-bit values by hand -- argtypes / restype of every symbol
+    come from include/ovla_b200.h itself (`_lib.header_prototypes`)."""
+    import ctypes as C
+
+    from openvla_probe_b200 import _lib
+
+    protos = _lib.header_prototypes()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ovla_b200.h")).read(), flags=re.S)
+    assert sorted(protos) == sorted(set(re.findall(r"\b(ovla_[a-z0-9_]+)\s*\(", hdr)))
+    for name, (restype, argtypes) in protos.items():
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None and list(fn.argtypes) == argtypes, name
+        assert fn.restype is restype, name
+    # spot checks of the mapping: pitches are 64-bit, handles and buffers are pointers, floats stay floats
+    g = protos["ovla_gemm"][1]
+    assert g[1] is C.c_longlong and g[3] is C.c_longlong and g[10] is C.c_longlong and g[0] is C.c_void_p
+    assert protos["ovla_probe_adamw"][1][4] is C.c_longlong and protos["ovla_probe_adamw"][1][9] is C.c_float
+    assert protos["ovla_workspace_bytes"][0] is C.c_longlong and protos["ovla_last_error"][0] is C.c_char_p
+    assert protos["ovla_bind_weight"][1][1] is C.c_char_p
+
+
 def test_library_contains_blackwell_instructions():
     """The shipped binary is sm_100a SASS with tcgen05 / TMA / TMEM instructions (no PTX-JIT, no fallback arch)."""
     import shutil

@@ -321,3 +321,127 @@ def test_per_label_confusion_counts_on_device():
         want[k] = [(t & q).sum(), (~t & q).sum(), (t & ~q).sum(), (~t & ~q).sum()]
     assert counts.shape == (K, 4) and np.array_equal(counts, want)
     assert len(per_label_metrics(counts, keep.tolist())) == K
+
+
+# ----------------------------------------------------------------------------------------------- all layers at once
+def _oracle_model(kind, D, K, sd):
+    from oracle import probe_oracle as PO
+
+    m = PO.DualHeadProbe(D, K) if kind == "dual" else torch.nn.Linear(D, K)
+    m.load_state_dict(sd)
+    return m
+
+
+@pytest.mark.parametrize("kind", ["object", "spatial", "dual"])
+def test_grouped_trainer_follows_the_oracle_and_the_single_layer_trainer(kind):
+    """G probes trained concurrently (grouped GEMMs + fused deterministic BCE / bias-gradient kernel + grouped AdamW)
+    against (a) the oracle's loss (the reference scripts' expressions) + torch.optim.AdamW per layer on the same batch
+    order, (b) the per-layer device trainer.  Tolerances as for the single-layer path: TF32 GEMMs -> loss 1e-3 relative,
+    weights rel-L2 2e-3, accumulated update rel-L2 5e-2."""
+    from oracle import probe_oracle as PO
+    from openvla_probe_b200.probes import MultiLayerProbeTrainer, ProbeTrainer
+
+    G, B = 3, 256
+    X0, Y, keep = _data(N=900, spatial=(kind == "spatial"))
+    Xs = torch.stack([X0 * (1.0 + 0.25 * g) + 0.1 * g for g in range(G)])               # [G, N, D]
+    K, D = len(keep), X0.shape[1]
+    pw = torch.tensor(3.7) if kind == "dual" else (0.5 + 3 * torch.rand(K, generator=torch.Generator().manual_seed(5)))
+    torch.manual_seed(11)
+    singles = [ProbeTrainer(kind, D, K, pw, batch=B) for _ in range(G)]
+    inits = [t.state_dict() for t in singles]
+    multi = MultiLayerProbeTrainer(kind, G, D, K, pw, batch=B, init_states=inits)
+    models = [_oracle_model(kind, D, K, sd) for sd in inits]
+    opts = [torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4) for m in models]
+    drop_last = kind == "dual"
+    gen = torch.Generator().manual_seed(9)
+    Xd, Yd = Xs.cuda(), Y.cuda()
+    for epoch in range(2):
+        perm = torch.randperm(X0.shape[0], generator=gen)
+        multi.load_epoch(Xd, Yd, keep, perm, drop_last)
+        for g in range(G):
+            singles[g].load_epoch(Xd[g], Yd, keep, perm, drop_last)
+        assert len(multi.steps) == len(singles[0].steps) == (X0.shape[0] // B if drop_last else -(-X0.shape[0] // B))
+        for s in range(len(multi.steps)):
+            idx = perm[s * B:(s + 1) * B]
+            ref_losses = []
+            for g in range(G):
+                loss, _ = PO.loss_fn(kind, models[g], Xs[g][idx], Y[idx][:, keep], pw)
+                opts[g].zero_grad(); loss.backward(); opts[g].step()
+                ref_losses.append(float(loss))
+                singles[g].train_step(s)
+            multi.train_step(s)
+            got = multi.step_losses()
+            np.testing.assert_allclose(got, ref_losses, rtol=1e-3, atol=1e-5)
+            np.testing.assert_allclose(got, [t.step_loss() for t in singles], rtol=2e-4, atol=1e-6)
+    multi.finish()
+    for g in range(G):
+        sd, ref, one = multi.state_dict(g), models[g].state_dict(), singles[g].state_dict()
+        for k in ref:
+            a, r, i0 = sd[k].float(), ref[k].float(), inits[g][k].float()
+            assert float((a - r).norm() / r.norm()) < 2e-3, (kind, g, k)
+            assert float(((a - i0) - (r - i0)).norm() / (r - i0).norm()) < 5e-2, (kind, g, k)
+            assert float((a - one[k]).norm() / one[k].norm()) < 2e-3, (kind, g, k)
+    # padded rows / columns never move
+    assert float(multi.P[:, : multi.n_w].view(G, multi.rows, D)[:, K:multi.Kpad].abs().max()) == 0.0
+
+
+def test_grouped_step_is_deterministic_and_handles_ragged_batches():
+    """Two trainers with the same initial weights and batch order end bit-identical (the grouped BCE / bias-gradient kernel
+    reduces in a fixed order, no floating-point atomics); the last, ragged batch (n % 128 != 0, n % 4 != 0) is covered."""
+    from openvla_probe_b200.probes import MultiLayerProbeTrainer
+
+    G, B = 5, 192
+    X0, Y, keep = _data(N=777, D=128, L=70)
+    Xs = torch.stack([X0 + 0.05 * g for g in range(G)]).cuda()
+    K, D = len(keep), X0.shape[1]
+    pw = 0.5 + 3 * torch.rand(K, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(1)
+    a = MultiLayerProbeTrainer("object", G, D, K, pw, batch=B)
+    inits = [a.state_dict(g) for g in range(G)]
+    b = MultiLayerProbeTrainer("object", G, D, K, pw, batch=B, init_states=inits, chunks=2)
+    perm = torch.randperm(X0.shape[0], generator=torch.Generator().manual_seed(2))
+    for t in (a, b):
+        t.load_epoch(Xs, Y.cuda(), keep, perm, drop_last=False)
+        assert t.steps[-1][1] - t.steps[-1][0] == 777 % B
+        for s in range(len(t.steps)):
+            t.train_step(s)
+        t.finish()
+    assert torch.equal(a.P, b.P) and torch.equal(a.Gbuf, b.Gbuf)
+    assert bool(torch.isfinite(a.P).all())
+
+
+def test_full_size_grouped_probe_step_vs_fp32():
+    """BASELINE configs[3] shape for several layers at once: batch 4096, D = 4096, K = 439, dual heads -- logits and the
+    un-normalised gradient of every layer against fp32 torch on the device (TF32 tolerance 2e-3 rel-L2)."""
+    from openvla_probe_b200.probes import MultiLayerProbeTrainer
+
+    G, B, D, L = 4, 4096, 4096, 481
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(G, B, D, generator=g)
+    Y = torch.randint(-1, 2, (B, L), generator=g).to(torch.int8)
+    keep = torch.arange(439)
+    torch.manual_seed(0)
+    tr = MultiLayerProbeTrainer("dual", G, D, 439, torch.tensor(1.7), batch=B)
+    Xd = X.cuda()
+    tr.load_epoch(Xd, Y.cuda(), keep, torch.arange(B), drop_last=True)
+    P0 = tr.P.clone()
+    tr.train_step(0)
+    tr.finish()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Yk = Y[:, keep].cuda()
+    for gi in range(G):
+        W = P0[gi, : tr.n_w].view(tr.rows, D)
+        bias = P0[gi, tr.n_w:]
+        z = Xd[gi] @ W.t() + bias
+        zp, zt = z[:, :439], z[:, tr.Kpad:tr.Kpad + 439]
+        pres_t, truth_t, mask = (Yk != -1).float(), (Yk == 1).float(), (Yk != -1).float()
+        gp = (torch.sigmoid(zp) * (1 + 0.7 * pres_t) - 1.7 * pres_t)          # d/dz of pos-weighted BCE, un-normalised
+        gt = (torch.sigmoid(zt) - truth_t) * mask
+        dW_ref = torch.cat([gp.t() @ Xd[gi], gt.t() @ Xd[gi]])
+        dW = torch.cat([tr.Gbuf[gi, : tr.n_w].view(tr.rows, D)[:439], tr.Gbuf[gi, : tr.n_w].view(tr.rows, D)[tr.Kpad:tr.Kpad + 439]])
+        assert float((dW - dW_ref).norm() / dW_ref.norm()) < 2e-3, gi
+        db = tr.Gbuf[gi, tr.n_w: tr.n_total]
+        db_ref = torch.cat([gp.sum(0), gt.sum(0)])
+        assert float((torch.cat([db[:439], db[tr.Kpad:tr.Kpad + 439]]) - db_ref).norm() / db_ref.norm()) < 1e-4, gi
+        st = tr.Gbuf[gi, tr.n_total:]
+        assert float(st[1]) == B * 439 and float(st[3]) == float(mask.sum())

@@ -32,6 +32,6 @@ ncu --set full --clock-control none --import-source on -k regex:pool_tokens -s 3
 export OVLA_GRAPHS=0
 CMD1="python bench.py --batch 1 --steps 1 --warmup 1 --lite"
 $CMD1 > gpurun_out/${R}_plain_bs1.log 2>&1 || { echo "bs1 plain run failed"; tail -5 gpurun_out/${R}_plain_bs1.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:gemv_kernel -s 200 -c 5 \
+ncu --set full --clock-control none --import-source on -k regex:ovla_wstream_kernel -s 200 -c 5 \
     -o gpurun_out/${R}_gemv_bs1 -f $CMD1 > gpurun_out/${R}_ncu_gemv.log 2>&1
 ls -la gpurun_out/ | grep ${R}_ | tail -20
