@@ -176,15 +176,29 @@ int probe_bce_grad_launch(const float* Z, long long ldz, const signed char* Y, i
 //   Z    [groups][n][ldz]  (z_gs apart)      dZT [groups][heads*Kpad][ldt]  (dzt_gs apart)
 //   db   = out_base + g*out_gs + db_off      stats = out_base + g*out_gs + stats_off   (the flat [dW | db | stats] buffer)
 //   part [groups][isplits][heads*Kpad + 4*ktiles] floats, ticket [groups] ints (zero on entry, left zero)
-__global__ void __launch_bounds__(256) bce_grad_grouped_kernel(const float* __restrict__ Z, long long ldz, long long z_gs,
-                                                               const signed char* __restrict__ Y, int n, int K, int Kpad,
-                                                               int kind0, int heads, const float* __restrict__ pos_weight,
-                                                               float pos_weight_scalar, float* __restrict__ dZT,
-                                                               long long ldt, long long dzt_gs, float* __restrict__ out_base,
-                                                               long long out_gs, long long db_off, long long stats_off,
-                                                               float* __restrict__ part, int* __restrict__ ticket) {
+// sp = softplus(-z) = log(1 + exp(-z)) and sig = sigmoid(z) from ONE exponential e = exp(-|z|) in (0, 1]:
+//   sp = log(1 + e) + max(-z, 0),  sig = z >= 0 ? 1 / (1 + e) : e / (1 + e).
+// ex2 / lg2 / rcp run on the SFU; 1 + e lies in (1, 2], where lg2.approx is accurate to ~1e-7 absolute, which is the
+// error that matters for a loss that is a SUM of such terms (tests: loss 1e-3 relative, gradients at fp32 round-off).
+__device__ __forceinline__ void softplus_neg_sigmoid(float z, float& sp, float& sig) {
+  const float e = __expf(-fabsf(z));
+  const float d = 1.f + e;
+  const float r = __frcp_rn(d);
+  sp = __logf(d) + fmaxf(-z, 0.f);
+  sig = z >= 0.f ? r : e * r;
+}
+
+template <int KIND0, int HEADS>
+__global__ void __launch_bounds__(256, 3) bce_grad_grouped_kernel(const float* __restrict__ Z, long long ldz, long long z_gs,
+                                                                  const signed char* __restrict__ Y, int n, int K, int Kpad,
+                                                                  const float* __restrict__ pos_weight,
+                                                                  float pos_weight_scalar, float* __restrict__ dZT,
+                                                                  long long ldt, long long dzt_gs, float* __restrict__ out_base,
+                                                                  long long out_gs, long long db_off, long long stats_off,
+                                                                  float* __restrict__ part, int* __restrict__ ticket) {
   constexpr int TI = 128;
-  __shared__ float tile[2][TI][33];
+  constexpr int kind0 = KIND0, heads = HEADS;
+  __shared__ float tile[HEADS][TI][33];
   __shared__ float red[8][8][32];   // [value: db0, db1, stats 0..3 -> rows 2..5][warp][lane]
   __shared__ int s_last;
   const int ktiles = gridDim.x, isplits = gridDim.y, grp = blockIdx.z;
@@ -200,18 +214,28 @@ __global__ void __launch_bounds__(256) bce_grad_grouped_kernel(const float* __re
   const float pw = (kind0 == 2) ? pos_weight_scalar : (k_ok ? pos_weight[k] : 1.f);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float db0 = 0.f, db1 = 0.f;
+  // store phase: thread -> (label row r0 + 2j, sample column sc) of the [32 x 128] transposed tile
+  const int sr0 = threadIdx.x >> 7, sc = threadIdx.x & 127;
+  const long long ldz8 = 8 * ldz, ldt2 = 2 * ldt;
   for (int it = it0; it < it1; ++it) {
     const int i0 = it * TI;
+    const bool full = i0 + TI <= n;
     // all loads of the tile first (16 independent rows per thread), then the math
     int yv[16];
     float z0[16], z1[16];
+    {
+      const float* zp = Z + static_cast<long long>(i0 + ty) * ldz + k;
+      const signed char* yp = Y + static_cast<long long>(i0 + ty) * Kpad + k;
+      const int ystep = 8 * Kpad;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int i = i0 + ty + 8 * j;
-      const bool ok = k_ok && i < n;
-      yv[j] = ok ? Y[static_cast<long long>(i) * Kpad + k] : -2;
-      z0[j] = ok ? Z[static_cast<long long>(i) * ldz + k] : 0.f;
-      z1[j] = (ok && heads == 2) ? Z[static_cast<long long>(i) * ldz + Kpad + k] : 0.f;
+      for (int j = 0; j < 16; ++j) {
+        const bool ok = k_ok && (full || i0 + ty + 8 * j < n);
+        yv[j] = ok ? static_cast<int>(*yp) : -2;
+        z0[j] = ok ? __ldcs(zp) : 0.f;
+        if (HEADS == 2) z1[j] = ok ? __ldcs(zp + Kpad) : 0.f;
+        zp += ldz8;
+        yp += ystep;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -225,17 +249,17 @@ __global__ void __launch_bounds__(256) bce_grad_grouped_kernel(const float* __re
           else if (kind0 == 1) { t = static_cast<float>(y); valid = 1.f; }
           else { t = (y != -1); valid = 1.f; }
           const float lw = 1.f + (pw - 1.f) * t;
-          const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);
-          const float sig = 1.f / (1.f + expf(-z));
+          float sp, sig;
+          softplus_neg_sigmoid(z, sp, sig);
           acc[0] += valid * ((1.f - t) * z + lw * sp);
           acc[1] += valid;
           g0 = valid * (sig * lw - pw * t);
         }
-        if (heads == 2) {
+        if (HEADS == 2) {
           const float z = z1[j];
           const float t = (y == 1), valid = (y != -1);
-          const float sp = log1pf(expf(-fabsf(z))) + fmaxf(-z, 0.f);
-          const float sig = 1.f / (1.f + expf(-z));
+          float sp, sig;
+          softplus_neg_sigmoid(z, sp, sig);
           acc[2] += valid * ((1.f - t) * z + sp);
           acc[3] += valid;
           g1 = valid * (sig - t);
@@ -244,18 +268,21 @@ __global__ void __launch_bounds__(256) bce_grad_grouped_kernel(const float* __re
       db0 += g0;
       db1 += g1;
       tile[0][ty + 8 * j][tx] = g0;
-      if (heads == 2) tile[1][ty + 8 * j][tx] = g1;
+      if (HEADS == 2) tile[HEADS - 1][ty + 8 * j][tx] = g1;
     }
     __syncthreads();
     // transposed store: label row k0 + r, 128 consecutive samples (4 lanes-of-32 segments per row)
+    if (i0 + sc < n) {
+      float* dp = dZT + static_cast<long long>(k0 + sr0) * ldt + i0 + sc;
+      const int r_end = min(32, Kpad - k0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int idx = threadIdx.x + 256 * j;    // 32 label rows x 128 samples
-      const int r = idx >> 7, c = idx & 127;
-      const int kk = k0 + r, i = i0 + c;
-      if (kk < Kpad && i < n) {
-        dZT[static_cast<long long>(kk) * ldt + i] = tile[0][c][r];
-        if (heads == 2) dZT[static_cast<long long>(Kpad + kk) * ldt + i] = tile[1][c][r];
+      for (int j = 0; j < 16; ++j) {
+        const int r = sr0 + 2 * j;
+        if (r < r_end) {
+          __stcs(dp, tile[0][sc][r]);
+          if (HEADS == 2) __stcs(dp + static_cast<long long>(Kpad) * ldt, tile[HEADS - 1][sc][r]);
+        }
+        dp += ldt2;
       }
     }
     __syncthreads();
@@ -327,8 +354,16 @@ int probe_bce_grad_grouped_launch(const float* Z, long long ldz, long long z_gs,
   if (!part || !ticket || !out_base) return set_error("probe: null workspace");
   dim3 grid((Kpad + 31) / 32, isplits, groups);
   ProfScope prof(kCatOther, 0.0, (8.0 * heads + 1.0) * n * Kpad * groups, st);
-  bce_grad_grouped_kernel<<<grid, 256, 0, st>>>(Z, ldz, z_gs, Y, n, K, Kpad, kind0, heads, pos_weight, pos_weight_scalar,
-                                                dZT, ldt, dzt_gs, out_base, out_gs, db_off, stats_off, part, ticket);
+#define OVLA_BCE_GROUPED(KD, HD)                                                                                        \
+  bce_grad_grouped_kernel<KD, HD><<<grid, 256, 0, st>>>(Z, ldz, z_gs, Y, n, K, Kpad, pos_weight, pos_weight_scalar, dZT, ldt, \
+                                                        dzt_gs, out_base, out_gs, db_off, stats_off, part, ticket)
+  if (heads == 2) {
+    if (kind0 != 2) return set_error("probe: the two-head form is the dual probe (kind0 = 2)");
+    OVLA_BCE_GROUPED(2, 2);
+  } else if (kind0 == 0) OVLA_BCE_GROUPED(0, 1);
+  else if (kind0 == 1) OVLA_BCE_GROUPED(1, 1);
+  else OVLA_BCE_GROUPED(2, 1);
+#undef OVLA_BCE_GROUPED
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
@@ -355,30 +390,58 @@ int probe_rowsum_launch(const float* A, long long lda, int rows, int cols, float
 }
 
 // ------------------------------------------------------------------------------------------- AdamW
-// torch.optim.AdamW (decoupled weight decay), one thread per parameter.  params = [W (rows x D) | b (rows)] in one
-// flat buffer, grads likewise (un-normalised); row r of head h is divided by stats[2h+1], the global number of
-// loss terms of that head -- read from device memory, so no host sync separates loss and update.
-// Grouped form: `groups` probes with parameters n_total apart and gradients / statistics g_gs / stats_gs apart.
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g_all, float* __restrict__ m,
-                             float* __restrict__ v, long long n_w, int D, int rows_per_head, long long n_total,
-                             const float* __restrict__ stats_all, float lr, float beta1, float beta2, float eps, float wd,
-                             float bc1, float bc2_sqrt, int groups, long long g_gs, long long stats_gs) {
-  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_total * groups) return;
-  const long long grp = i / n_total, j = i - grp * n_total;
-  const float* g = g_all + grp * g_gs - grp * n_total;   // so that g[i] below addresses this group's gradient j
+// torch.optim.AdamW (decoupled weight decay).  params = [W (rows x D) | b (rows)] in one flat buffer, grads likewise
+// (un-normalised); row r of head h is divided by stats[2h+1], the global number of loss terms of that head -- read from
+// device memory, so no host sync separates loss and update.
+// Grouped form: `groups` probes (blockIdx.y) with parameters n_total apart and gradients / statistics g_gs / stats_gs
+// apart.  One thread updates 4 consecutive parameters of W with 16-byte accesses (D % 4 == 0, so the 4 share a row);
+// the bias tail (and everything, when a base pointer is not 16-byte aligned) goes through the scalar path.
+__device__ __forceinline__ float adamw_one(float p, float grad, float& m, float& v, float lr, float beta1, float beta2,
+                                           float eps, float wd, float bc1, float bc2_sqrt) {
+  p *= (1.f - lr * wd);
+  m = beta1 * m + (1.f - beta1) * grad;
+  v = beta2 * v + (1.f - beta2) * grad * grad;
+  return p - (lr / bc1) * m / (sqrtf(v) / bc2_sqrt + eps);
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p_all, const float* __restrict__ g_all,
+                                                    float* __restrict__ m_all, float* __restrict__ v_all, long long n_w, int D,
+                                                    int rows_per_head, long long n_total, const float* __restrict__ stats_all,
+                                                    float lr, float beta1, float beta2, float eps, float wd, float bc1,
+                                                    float bc2_sqrt, long long g_gs, long long stats_gs, int vec) {
+  const long long grp = blockIdx.y;
+  float* p = p_all + grp * n_total;
+  float* m = m_all + grp * n_total;
+  float* v = v_all + grp * n_total;
+  const float* g = g_all + grp * g_gs;
   const float* stats = stats_all + grp * stats_gs;
-  const long long row = (j < n_w) ? j / D : j - n_w;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_vec = vec ? n_w / 4 : 0;                     // float4 items of the W block
+  if (t < n_vec) {
+    const long long j = t * 4;
+    const int head = static_cast<int>((j / D) / rows_per_head);
+    const float denom = stats[2 * head + 1];
+    float4 pp = *reinterpret_cast<const float4*>(p + j), gg = __ldcs(reinterpret_cast<const float4*>(g + j));
+    float4 mm = *reinterpret_cast<const float4*>(m + j), vv = *reinterpret_cast<const float4*>(v + j);
+    pp.x = adamw_one(pp.x, denom > 0.f ? gg.x / denom : 0.f, mm.x, vv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    pp.y = adamw_one(pp.y, denom > 0.f ? gg.y / denom : 0.f, mm.y, vv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    pp.z = adamw_one(pp.z, denom > 0.f ? gg.z / denom : 0.f, mm.z, vv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    pp.w = adamw_one(pp.w, denom > 0.f ? gg.w / denom : 0.f, mm.w, vv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    *reinterpret_cast<float4*>(p + j) = pp;
+    *reinterpret_cast<float4*>(m + j) = mm;
+    *reinterpret_cast<float4*>(v + j) = vv;
+    return;
+  }
+  const long long i = n_vec * 4 + (t - n_vec);                  // scalar tail
+  if (i >= n_total) return;
+  const long long row = (i < n_w) ? i / D : i - n_w;
   const int head = static_cast<int>(row / rows_per_head);
   const float denom = stats[2 * head + 1];  // global count of the head's loss terms (after the allreduce)
   const float grad = denom > 0.f ? g[i] / denom : 0.f;
-  float pi = p[i] * (1.f - lr * wd);
-  const float mi = beta1 * m[i] + (1.f - beta1) * grad;
-  const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+  float mi = m[i], vi = v[i];
+  p[i] = adamw_one(p[i], grad, mi, vi, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
   m[i] = mi;
   v[i] = vi;
-  pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
-  p[i] = pi;
 }
 
 int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n_w, int D, int rows_per_head,
@@ -389,9 +452,15 @@ int probe_adamw_launch(float* p, const float* g, float* m, float* v, long long n
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   ProfScope prof(kCatOther, 0.0, 28.0 * n_total * groups, st);
-  adamw_kernel<<<static_cast<unsigned>((n_total * groups + 255) / 256), 256, 0, st>>>(
-      p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, bc1, static_cast<float>(sqrt(bc2)),
-      groups, g_gs, stats_gs);
+  // 16-byte path for the W block when every base and group stride keeps float4 alignment
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int vec = (D % 4 == 0 && n_w % 4 == 0 && al16(p) && al16(g) && al16(m) && al16(v) &&
+                   (groups == 1 || (n_total % 4 == 0 && g_gs % 4 == 0))) ? 1 : 0;
+  const long long items = (vec ? n_w / 4 : 0) + (n_total - (vec ? n_w : 0));
+  if (groups > 65535) return set_error("adamw: too many groups (%d)", groups);
+  dim3 grid(static_cast<unsigned>((items + 255) / 256), static_cast<unsigned>(groups));
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n_w, D, rows_per_head, n_total, stats, lr, beta1, beta2, eps, wd, bc1,
+                                     static_cast<float>(sqrt(bc2)), g_gs, stats_gs, vec);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
