@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--probe-kind", default="object", choices=["object", "spatial", "dual"])
     ap.add_argument("--probe-layers", type=int, default=33)
     ap.add_argument("--probe-chunks", type=int, default=0)
+    ap.add_argument("--probe-comm-sms", type=int, default=16, help="SMs the grouped GEMMs leave to the collective at N > 1")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--lite", action="store_true",
                     help="profiling mode for ncu: exactly --warmup untimed steps, no e2e / bs1 / CPU legs")
@@ -248,7 +249,7 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------- probe-training leg
 def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str = "object", G: int = 33, batch: int = 4096,
-                       D: int = 4096, K: int = 439, steps: int = 12, warmup: int = 3, chunks: int = 0):
+                       D: int = 4096, K: int = 439, steps: int = 12, warmup: int = 3, chunks: int = 0, comm_sms: int = 16):
     """BASELINE.json configs[3]: linear (object) probes of all 33 captured layers trained concurrently on synthetic
     4096-d features, multilabel BCE, AdamW; at N > 1 every rank takes its own batch of 4096 rows per layer-step (weak
     scaling, global batch 4096 x N) and the flat [dW | db | stats] gradients go through NCCL all-reduce, chunked and
@@ -267,7 +268,7 @@ def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str 
     keep = torch.arange(K)
     torch.manual_seed(0)
     pw = torch.tensor(1.7) if kind == "dual" else torch.ones(K) * 2.0
-    tr = MultiLayerProbeTrainer(kind, G, D, K, pw, batch=batch, device=local, chunks=chunks, shard="local")
+    tr = MultiLayerProbeTrainer(kind, G, D, K, pw, batch=batch, device=local, chunks=chunks, shard="local", comm_sms=comm_sms)
     perm = torch.randperm(N, generator=torch.Generator().manual_seed(1))
     tr.load_epoch(X, Y, keep, perm, drop_last=True)
     del X
@@ -323,7 +324,7 @@ def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str 
                              f"{flops_ls / 1e9:.1f} GFLOP per layer-step"},
         "allreduce": {"bytes_per_step": int(tr.Gbuf.numel() * 4) if world > 1 else 0, "chunks": len(tr.chunks),
                       "alone_ms": ar_ms, "overlapped": world > 1 and len(tr.chunks) > 1,
-                      "sm_limit_of_gemms": tr.sm_limit},
+                      "sm_limit_of_gemms": tr.sm_limit, "NCCL_MAX_CTAS": os.environ.get("NCCL_MAX_CTAS")},
         "loss_layer0": losses[0],
     }
     del tr
@@ -353,12 +354,16 @@ def main():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # the probe-training all-reduce runs BESIDE persistent GEMMs that leave it `--probe-comm-sms` SMs: keep NCCL's
+        # grid within that reservation (the data path of the capture benchmark itself has no collective)
+        os.environ.setdefault("NCCL_MAX_CTAS", str(max(1, args.probe_comm_sms)))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
 
     if args.probe_only:
         blk = probe_training_leg(world, rank, local, lib, load_peaks(), kind=args.probe_kind, G=args.probe_layers,
-                                 steps=args.steps, warmup=args.warmup, chunks=args.probe_chunks)
+                                 steps=args.steps, warmup=args.warmup, chunks=args.probe_chunks,
+                                 comm_sms=args.probe_comm_sms)
         if rank == 0:
             print(json.dumps(blk), flush=True)
         if world > 1:
@@ -487,7 +492,7 @@ def main():
         del model
         torch.cuda.empty_cache()
         try:
-            probe_block = probe_training_leg(world, rank, local, lib, peaks)
+            probe_block = probe_training_leg(world, rank, local, lib, peaks, comm_sms=args.probe_comm_sms)
         except Exception as ex:  # noqa: BLE001 -- recorded, never takes the headline number down
             probe_block = {"error": f"{type(ex).__name__}: {ex}"}
         model = None
