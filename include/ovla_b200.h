@@ -156,6 +156,14 @@ void ovla_destroy(OvlaEngine* e);
  * engine's packed layout (q/k/v stacked, gate/up interleaved, patch-embed K padded).  Extra names:
  * "rope.cos" / "rope.sin" = bf16 [max_seq, head_dim/2] tables (LlamaRotaryEmbedding, cast to bf16).       */
 int ovla_bind_weight(OvlaEngine* e, const char* name, const void* src_dev, const long long* shape, int ndim);
+/* Execution options of one engine (A/B measurements and tests; results do not depend on them beyond what the tests
+ * state): "decode_mega" (1: a cached decode step at batch <= 4 is one persistent kernel; 0: per-layer kernels),
+ * "attn_tc", "fuse_rope", "two_streams", "graph_max_batch" (largest batch replayed from a CUDA graph; 0 = eager).
+ * Drops the engine's captured CUDA graphs.                                                                     */
+int ovla_set_option(OvlaEngine* e, const char* name, int value);
+/* Debug: %globaltimer stamps (ns) of the last persistent decode step, [2][1024] = first and last CTA, one stamp per
+ * phase edge (engine created with OVLA_MEGA_TRACE=1 in the environment); tools/decode_trace.py prints the timeline. */
+int ovla_debug_decode_trace(OvlaEngine* e, unsigned long long* out_host, int n);
 /* verifies that every tensor the path needs has been bound */
 int ovla_finalize(OvlaEngine* e);
 long long ovla_workspace_bytes(const OvlaEngine* e);

@@ -93,6 +93,11 @@ struct OvlaEngine {
   int* err_flag = nullptr;
   // split-K partial-tile scratch, one per stream this engine issues GEMMs on (never shared with another engine)
   SplitKWs ws_main = {nullptr, 0}, ws_side = {nullptr, 0};
+  // persistent decode-step kernel (decode_mega.cu): per-layer weight pointers + the grid-barrier counter on the device
+  DecodeLayerPtrs* mega_layers = nullptr;
+  unsigned* mega_barrier = nullptr;
+  unsigned long long* mega_trace = nullptr;   // OVLA_MEGA_TRACE=1: phase timeline of the last persistent decode step
+  bool decode_mega = true;   // OVLA_DECODE_MEGA=0: per-layer kernels
   // CUDA-graph cache for launch-bound small batches (see ovla_run)
   int graph_max_batch = 16;
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
@@ -163,6 +168,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   if (const char* tc = getenv("OVLA_ATTN_TC")) e->attn_tc = tc[0] != '0';
   if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
   if (const char* ts = getenv("OVLA_TWO_STREAMS")) e->two_streams = ts[0] != '0';
+  if (const char* dm = getenv("OVLA_DECODE_MEGA")) e->decode_mega = dm[0] != '0';
   if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
   e->device = device;
   const OvlaDims& d = e->d;
@@ -258,6 +264,9 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   W(&e->logits, B * d.vocab);
   W(&e->tokens, 64LL * B);
   W(&e->err_flag, 4);
+  W(&e->mega_layers, std::max(1, d.llm_layers));
+  W(&e->mega_barrier, 4);
+  if (getenv("OVLA_MEGA_TRACE")) W(&e->mega_trace, 2 * 1024);
   {
     // split-K runs only for M <= 512 rows (gemm.cu): S <= 8 slices of [M, N] fp32; sized for the widest such GEMM
     // (the vocabulary / gate_up for the LLM stream, the tower MLP for the side stream), capped at 192 MB
@@ -428,6 +437,30 @@ extern "C" int ovla_bind_weight(OvlaEngine* e, const char* cname, const void* sr
   return set_error("bind %s: unknown tensor name", cname);
 }
 
+extern "C" int ovla_debug_decode_trace(OvlaEngine* e, unsigned long long* out_host, int n) {
+  if (!e || !out_host) return set_error("ovla_debug_decode_trace: null argument");
+  if (!e->mega_trace) return set_error("ovla_debug_decode_trace: create the engine with OVLA_MEGA_TRACE=1");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out_host, e->mega_trace, sizeof(unsigned long long) * std::min(n, 2048), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ovla_set_option(OvlaEngine* e, const char* name, int value) {
+  if (!e || !name) return set_error("ovla_set_option: null argument");
+  const std::string n(name);
+  if (n == "decode_mega") e->decode_mega = value != 0;
+  else if (n == "attn_tc") e->attn_tc = value != 0;
+  else if (n == "fuse_rope") e->fuse_rope = value != 0;
+  else if (n == "two_streams") e->two_streams = value != 0;
+  else if (n == "graph_max_batch") e->graph_max_batch = value;
+  else return set_error("ovla_set_option: unknown option '%s'", name);
+  // captured passes embed the old choice
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+  return 0;
+}
+
 extern "C" int ovla_finalize(OvlaEngine* e) {
   if (!e) return set_error("ovla_finalize: null engine");
   std::string missing;
@@ -468,6 +501,15 @@ extern "C" int ovla_finalize(OvlaEngine* e) {
   }
   if (n_missing) return set_error("ovla_finalize: %d tensors not bound (%s%s)", n_missing, missing.c_str(),
                                   n_missing > 6 ? ", ..." : "");
+  {  // weight-pointer table of the persistent decode-step kernel
+    std::vector<DecodeLayerPtrs> tab(e->layers.size());
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+      LayerW& l = e->layers[i];
+      tab[i] = DecodeLayerPtrs{l.ln1.ptr, l.qkv_w.ptr, l.o_w.ptr, l.ln2.ptr, l.gate_up_w.ptr, l.down_w.ptr};
+    }
+    if (e->mega_layers && !tab.empty())
+      CUDA_TRY(cudaMemcpy(e->mega_layers, tab.data(), sizeof(DecodeLayerPtrs) * tab.size(), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   return 0;
 }
@@ -608,6 +650,22 @@ int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t s
   const OvlaDims& d = e->d;
   const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim;
   const int Tmax = d.max_seq;
+  if (e->decode_mega && B <= 4 && e->mega_layers && !prof_enabled()) {
+    // batch <= 4: the whole step as one persistent kernel with a continuous weight stream (decode_mega.cu)
+    DecodeStepArgs a = {};
+    a.layers = e->mega_layers;
+    a.final_norm = e->final_norm.ptr; a.lm_head = e->lm_head.ptr;
+    a.rope_cos = e->rope_cos.ptr; a.rope_sin = e->rope_sin.ptr;
+    a.x = e->l_x; a.qkv = e->l_qkv; a.attn = e->l_attn; a.act = e->l_act;
+    a.kv = e->kv; a.kv_layer_elems = e->kv_layer_elems();
+    a.logits = logits; a.barrier = e->mega_barrier;
+    a.trace = e->mega_trace; a.trace_stride = 1024;
+    { static const int dbg = getenv("OVLA_MEGA_DBG") ? atoi(getenv("OVLA_MEGA_DBG")) : 0; a.dbg = dbg; }
+    a.n_layers = d.llm_layers; a.M = B; a.D = D; a.I = d.llm_inter; a.H = H; a.head_dim = hd; a.vocab = d.vocab;
+    a.Tmax = Tmax; a.pos = pos; a.eps = d.rms_eps;
+    const int rc = decode_step_launch(a, st);
+    if (rc != -2) return rc;
+  }
   for (int i = 0; i < d.llm_layers; ++i) {
     LayerW& l = e->layers[i];
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, B, D, st));

@@ -27,6 +27,28 @@ int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void
 SplitKWs splitk_stream_workspace(cudaStream_t st);
 int splitk_epilogue_launch(int mode, const float* ws, long long slice_stride, long long ldw, int S, int M, int N,
                            const GemmEpi& epi, cudaStream_t st);
+// decode_mega.cu -- one cached decode step (batch <= 4) as one persistent kernel
+struct DecodeLayerPtrs {
+  const __nv_bfloat16 *ln1, *qkv, *o, *ln2, *gate_up, *down;   // packed [N, K] weights (gate_up rows interleaved 32/32)
+};
+struct DecodeStepArgs {
+  const DecodeLayerPtrs* layers;        // device array [n_layers]
+  const __nv_bfloat16 *final_norm, *lm_head, *rope_cos, *rope_sin;
+  __nv_bfloat16 *x, *qkv, *attn, *act;  // [M, D] residual (in/out), [M, 3D], [M, D], [M, I] scratch
+  __nv_bfloat16* kv;                    // KV cache base; layer stride kv_layer_elems, V half at + kv_layer_elems / 2
+  long long kv_layer_elems;
+  float* logits;                        // [M, vocab] fp32
+  unsigned* barrier;                    // one counter, zeroed by the launcher
+  int n_layers, M, D, I, H, head_dim, vocab, Tmax, pos;
+  float eps;
+  unsigned long long* trace;            // optional timeline buffer [2][trace_stride] (debug), else null
+  int trace_stride;
+  int dbg;                              // debug bits (OVLA_MEGA_DBG): 1 = skip the dot products, 2 = skip attention (wrong results)
+  // filled by the launcher
+  int S, attn_floats;
+  float attn_scale;
+};
+int decode_step_launch(DecodeStepArgs a, cudaStream_t st);
 // gemv.cu -- M <= 8 weight streaming
 int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, int mode,
                 const GemmEpi& epi, cudaStream_t st);

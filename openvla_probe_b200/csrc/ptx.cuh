@@ -128,6 +128,20 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(const CUtensorMap* m, uint
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// bulk prefetch of [p, p + bytes) into L2 (16-byte aligned, bytes a multiple of 16): no destination, no completion
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared::cta of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted
+// on an mbarrier of this CTA; `policy`: L2 eviction-priority hint (weights that are read once: kL2EvictFirst)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                             unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
@@ -317,6 +331,35 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+// ---- dot products of the weight-streaming kernels (gemv.cu, decode_mega.cu): ONE summation order for all of them.
+// A lane walks the 16-byte chunks lane, lane + 32, ... of a weight row in ascending order; within a chunk the eight
+// products go to eight independent fp32 chains (element position e of every chunk -> chain e, as four packed FFMA2), so
+// the critical path per chunk is one FMA instead of eight; the chains are combined in the fixed order below, then the
+// lanes by an xor-shuffle tree.
+struct WsAcc {
+  uint64_t a[4];   // f32x2 accumulators: chains (2j, 2j + 1)
+};
+__device__ __forceinline__ void wstream_zero(WsAcc& c) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c.a[j] = 0ull;
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) {
+  return pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void wstream_fma8(const uint4& wv, const uint4& xv, WsAcc& c) {
+  c.a[0] = fma_f32x2(bf16x2_to_f32x2(wv.x), bf16x2_to_f32x2(xv.x), c.a[0]);
+  c.a[1] = fma_f32x2(bf16x2_to_f32x2(wv.y), bf16x2_to_f32x2(xv.y), c.a[1]);
+  c.a[2] = fma_f32x2(bf16x2_to_f32x2(wv.z), bf16x2_to_f32x2(xv.z), c.a[2]);
+  c.a[3] = fma_f32x2(bf16x2_to_f32x2(wv.w), bf16x2_to_f32x2(xv.w), c.a[3]);
+}
+__device__ __forceinline__ float wstream_combine(const WsAcc& c) {
+  float x0, y0, x1, y1, x2, y2, x3, y3;
+  unpack_f32x2(c.a[0], x0, y0);
+  unpack_f32x2(c.a[1], x1, y1);
+  unpack_f32x2(c.a[2], x2, y2);
+  unpack_f32x2(c.a[3], x3, y3);
+  return ((x0 + y0) + (x1 + y1)) + ((x2 + y2) + (x3 + y3));
 }
 
 __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {

@@ -150,6 +150,10 @@ class Engine:
             C.c_void_p(tokens_out_host.data_ptr()) if tokens_out_host is not None else None,
             _lib.stream_ptr()))
 
+    def set_option(self, name: str, value: int) -> None:
+        """ovla_set_option: "decode_mega", "attn_tc", "fuse_rope", "two_streams", "graph_max_batch"."""
+        _lib.check(self.lib.ovla_set_option(self._h, name.encode(), int(value)))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self.lib.ovla_destroy(self._h)

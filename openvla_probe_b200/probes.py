@@ -838,9 +838,12 @@ def _evaluate_host(kind: str, trainer: ProbeTrainer, X: torch.Tensor, Y: torch.T
 
 # ----------------------------------------------------------------------------------------------- per-layer driver
 def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 20, batch: int = 4096, device: int = 0,
-                 out_dir: str = ".", exclude: Sequence[int] = (), seed: int = 0, group=None, verbose: bool = True):
+                 out_dir: str = ".", exclude: Sequence[int] = (), seed: int = 0, group=None, verbose: bool = True,
+                 concurrent: bool = True, hbm_budget_gb: float = 120.0):
     """Per-layer loop of the three reference scripts (train_object_probes.py:208-232, train_spatial_probes.py:179-204,
-    train_dual_head_final.py:236-290).  Rank 0 writes the `.pth` files and the CSV."""
+    train_dual_head_final.py:236-290).  Rank 0 writes the `.pth` files and the CSV.  `concurrent`: the probes of all
+    requested layers train at the same time on shared shuffled batches (MultiLayerProbeTrainer) instead of one after the
+    other; the per-layer results are the same training procedure, only the shuffle is common to the layers."""
     import pandas as pd
 
     cache = load_episodes(log_dir, exclude)
@@ -854,35 +857,72 @@ def train_probes(kind: str, log_dir: str, layers: Sequence[int], epochs: int = 2
         torch.manual_seed(seed)
     records = []
     rank0 = True
-    for L in layers:
-        Xtr, Ytr = layer_matrix(cache, split.train_ids, L)
-        Xva, Yva = layer_matrix(cache, split.val_ids, L)
-        if Xtr.shape[0] == 0 or Xva.shape[0] == 0:
-            records.append(dict(layer=L, status="skipped_empty_data"))
-            continue
-        tr = ProbeTrainer(kind, Xtr.shape[1], len(split.keep), split.pos_weight, batch=batch, device=device, group=group)
-        rank0 = tr.rank == 0
-        tr.fit(Xtr, Ytr, split.keep, epochs, seed=seed + L, drop_last=(kind in (KIND_DUAL, KIND_3CLASS)))
-        rec = dict(layer=L, **evaluate(kind, tr, Xva, Yva, split.keep))
-        records.append(rec)
-        if rank0:
-            os.makedirs(out_dir, exist_ok=True)
-            if kind == KIND_3CLASS:
-                torch.save({"model_type": "Direct3ClassProbe", "state_dict": tr.state_dict(), "layer": L,
-                            "kept_indices": split.keep.tolist(), "input_dim": tr.D, "num_output_labels_probed": tr.K,
-                            "num_classes_per_label": 3, "class_weights_used": [float(v) for v in split.pos_weight],
-                            "class_mapping": {"NA(-1)": 0, "False(0)": 1, "True(1)": 2}},
-                           os.path.join(out_dir, f"linear_probe_3class_direct_L{L:02d}.pth"))
-            elif kind == KIND_DUAL:
-                torch.save({"model_type": "DualHeadProbe", "state_dict": tr.state_dict(), "layer": L,
-                            "kept_indices": split.keep.tolist(), "input_dim": tr.D, "num_output_labels": tr.K,
-                            "presence_pos_weight_used": float(split.pos_weight)},
-                           os.path.join(out_dir, f"linear_probe_dual_head_final_L{L:02d}.pth"))
-            else:
-                torch.save({"state_dict": tr.state_dict(), "layer": L, "kept": split.keep.tolist()},
-                           os.path.join(out_dir, f"linear_probe_L{L:02d}.pth"))
-            if verbose:
-                print(f"L{L:02d}  " + "  ".join(f"{k}={v:.3f}" for k, v in rec.items() if k != "layer"))
+
+    def _save(L, tr_state, D_, rec):
+        os.makedirs(out_dir, exist_ok=True)
+        K_ = len(split.keep)
+        if kind == KIND_3CLASS:
+            torch.save({"model_type": "Direct3ClassProbe", "state_dict": tr_state, "layer": L,
+                        "kept_indices": split.keep.tolist(), "input_dim": D_, "num_output_labels_probed": K_,
+                        "num_classes_per_label": 3, "class_weights_used": [float(v) for v in split.pos_weight],
+                        "class_mapping": {"NA(-1)": 0, "False(0)": 1, "True(1)": 2}},
+                       os.path.join(out_dir, f"linear_probe_3class_direct_L{L:02d}.pth"))
+        elif kind == KIND_DUAL:
+            torch.save({"model_type": "DualHeadProbe", "state_dict": tr_state, "layer": L,
+                        "kept_indices": split.keep.tolist(), "input_dim": D_, "num_output_labels": K_,
+                        "presence_pos_weight_used": float(split.pos_weight)},
+                       os.path.join(out_dir, f"linear_probe_dual_head_final_L{L:02d}.pth"))
+        else:
+            torch.save({"state_dict": tr_state, "layer": L, "kept": split.keep.tolist()},
+                       os.path.join(out_dir, f"linear_probe_L{L:02d}.pth"))
+        if verbose:
+            print(f"L{L:02d}  " + "  ".join(f"{k}={v:.3f}" for k, v in rec.items() if k != "layer"))
+
+    drop_last = kind in (KIND_DUAL, KIND_3CLASS)
+    mats = {L: (layer_matrix(cache, split.train_ids, L), layer_matrix(cache, split.val_ids, L)) for L in layers}
+    live = [L for L in layers if mats[L][0][0].shape[0] and mats[L][1][0].shape[0]]
+    same = len({(tuple(mats[L][0][0].shape), tuple(mats[L][1][0].shape)) for L in live}) == 1
+    if concurrent and kind != KIND_3CLASS and len(live) > 1 and same:
+        # all layers at once (MultiLayerProbeTrainer): same labels, same shuffled batches, grouped kernels.  Layers are
+        # processed in groups that keep features + the two shuffled copies within `hbm_budget_gb`.
+        N, D_ = mats[live[0]][0][0].shape
+        per_layer = 3.0 * N * D_ * 4
+        gmax = max(1, int(hbm_budget_gb * 1e9 // per_layer))
+        done = {}
+        for i in range(0, len(live), gmax):
+            grp = live[i:i + gmax]
+            X = torch.stack([mats[L][0][0] for L in grp])
+            Ytr = mats[grp[0]][0][1]
+            tr = MultiLayerProbeTrainer(kind, len(grp), D_, len(split.keep), split.pos_weight, batch=batch, device=device,
+                                        group=group)
+            rank0 = tr.rank == 0
+            tr.fit(X, Ytr, split.keep, epochs, seed=seed, drop_last=drop_last)
+            for gi, L in enumerate(grp):
+                sd = tr.state_dict(gi)
+                ev = ProbeTrainer(kind, D_, len(split.keep), split.pos_weight, batch=batch, device=device, init_state=sd)
+                done[L] = (dict(layer=L, **evaluate(kind, ev, mats[L][1][0], mats[L][1][1], split.keep)), sd)
+            del tr, X
+            torch.cuda.empty_cache()
+        for L in layers:
+            if L not in done:
+                records.append(dict(layer=L, status="skipped_empty_data"))
+                continue
+            records.append(done[L][0])
+            if rank0:
+                _save(L, done[L][1], D_, done[L][0])
+    else:
+        for L in layers:
+            (Xtr, Ytr), (Xva, Yva) = mats[L]
+            if Xtr.shape[0] == 0 or Xva.shape[0] == 0:
+                records.append(dict(layer=L, status="skipped_empty_data"))
+                continue
+            tr = ProbeTrainer(kind, Xtr.shape[1], len(split.keep), split.pos_weight, batch=batch, device=device, group=group)
+            rank0 = tr.rank == 0
+            tr.fit(Xtr, Ytr, split.keep, epochs, seed=seed + L, drop_last=drop_last)
+            rec = dict(layer=L, **evaluate(kind, tr, Xva, Yva, split.keep))
+            records.append(rec)
+            if rank0:
+                _save(L, tr.state_dict(), tr.D, rec)
     if rank0:
         name = {KIND_OBJECT: "probe_metrics_object.csv", KIND_SPATIAL: "probe_metrics_spatial.csv",
                 KIND_DUAL: "probe_metrics_dual_head_final.csv", KIND_3CLASS: "probe_metrics_3class_direct.csv"}[kind]
@@ -899,6 +939,7 @@ def main():
     cli.add_argument("--layers", default="all", help="comma-sep list, e.g. 32 or 0,8,16,32; 'all' = 0-32")
     cli.add_argument("--exclude_eps", default="")
     cli.add_argument("--out_dir", default=".")
+    cli.add_argument("--sequential", action="store_true", help="one layer at a time, as the reference loops")
     args = cli.parse_args()
     layers = list(range(33)) if args.layers.strip().lower() == "all" else [int(x) for x in args.layers.split(",")]
     assert all(0 <= L <= 32 for L in layers), "layer index must be 0-32"
@@ -908,9 +949,10 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")     # the all-reduce runs beside GEMMs that leave it 16 SMs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     train_probes(args.kind, args.log_dir, layers, args.epochs, args.batch, device=local, out_dir=args.out_dir,
-                 exclude=sorted(parse_exclusions(args.exclude_eps)))
+                 exclude=sorted(parse_exclusions(args.exclude_eps)), concurrent=not args.sequential)
     if world > 1:
         import torch.distributed as dist
 
