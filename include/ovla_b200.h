@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define OVLA_ABI_VERSION 1
+#define OVLA_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ library */
 int ovla_abi_version(void);
@@ -97,6 +97,10 @@ int ovla_rope_kv(void* qkv_dev, int B, int T, int H, int head_dim, int pos0, con
  * mode 0 = mean over rows [0, n_rows), 1 = "final" (row n_rows-1). */
 int ovla_pool_tokens(const void* x_dev, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
                      float* out_dev, long long out_batch_stride, void* stream);
+/* the same for right-padded rows: row b pools over n_rows - (P - lens_dev[b]) rows ("pool over each
+ * sample's true length") */
+int ovla_pool_tokens_ragged(const void* x_dev, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                            const int* lens_dev, int P, float* out_dev, long long out_batch_stride, void* stream);
 /* torch.argmax(logits, -1) per row: first index of the maximum, NaN is maximal (greedy step of generate). */
 int ovla_argmax(const float* logits_dev, long long ld, int rows, int n, long long* out_dev, void* stream);
 /* de-tokenise + un-normalise (modeling_prismatic.py:521-534), float64, bit-identical to numpy. */
@@ -128,6 +132,10 @@ int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw
 int ovla_decode_rope_attention(const void* qkv_dev, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
                                void* k_cache_dev, void* v_cache_dev, int B, int H, int head_dim, int Tmax,
                                void* out_dev, long long o_ld, void* stream);
+/* the same step for a ragged batch: row b works at position pos - (P - lens_dev[b]) (int32 [B] lengths out of P) */
+int ovla_decode_rope_attention_ragged(const void* qkv_dev, long long qkv_ld, const void* cos_dev, const void* sin_dev,
+                                      int pos, const int* lens_dev, int P, void* k_cache_dev, void* v_cache_dev, int B,
+                                      int H, int head_dim, int Tmax, void* out_dev, long long o_ld, void* stream);
 
 /* ------------------------------------------------------------------ engine
  * Stands behind OpenVLAForActionPrediction (modeling_prismatic.py:491-562) + get_vla_action's capture
@@ -184,15 +192,23 @@ typedef struct OvlaRunArgs {
   void* hidden_out_dev;           /* bf16 [llm_layers+1, B, T, llm_dim] or NULL (forward(output_hidden_states)) */
   void* projector_out_dev;        /* bf16 [B, n_patches, llm_dim] or NULL                               */
   void* patches_out_dev;          /* bf16 [B, n_patches, vision_dim] or NULL (vision backbone output)   */
+  /* Ragged batch (the reference is batch-1 only, modeling_prismatic.py:326; its padded-batch splice is :388-390, SURVEY
+   * Appendix B): int32 [B] true prompt lengths in [1, P] of RIGHT-padded rows of input_ids (each row: its ids, then
+   * 29871, then any valid pad id), or NULL = every row has P ids.  Row b then pools over pool_len - (P - len_b) rows,
+   * takes its first token from position n_patches + len_b - 1 and decodes at its own positions, i.e. gives what a
+   * batch-1 call on its un-padded prompt gives (causal attention never looks at the pads). The lengths are read on
+   * the device at run time (a captured pass may be replayed with new lengths in the same buffer).                 */
+  const int* prompt_lens_dev;
 } OvlaRunArgs;
 
 /* device-resident inputs/outputs */
 int ovla_run(OvlaEngine* e, const OvlaRunArgs* args, void* stream);
 /* Same, with HOST buffers (pinned or pageable): copies inputs H2D, runs, copies pooled/tokens back D2H and
- * synchronises the stream.  This is the call the reference-facing predict_action makes.               */
+ * synchronises the stream.  This is the call the reference-facing predict_action makes.
+ * prompt_lens_host: int32 [B] or NULL, see OvlaRunArgs.prompt_lens_dev.                                */
 int ovla_run_host(OvlaEngine* e, const long long* input_ids_host, const void* pixel_values_host, int B, int P,
                   int pool_len, int pool_mode, int n_new_tokens, float* pooled_out_host, long long* tokens_out_host,
-                  void* stream);
+                  const int* prompt_lens_host, void* stream);
 
 /* ------------------------------------------------------------------ probe training
  * Kernels around the two TF32 tcgen05 GEMMs (ovla_gemm, OVLA_KIND_TF32) of one probe step:

@@ -52,9 +52,10 @@ class ShardedCollector:
         self.world, self.rank = world_info(group)
 
     def run_local(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, unnorm_key: Optional[str],
-                  layer_indices: Sequence[int], pooling_method: str = "mean"):
+                  layer_indices: Sequence[int], pooling_method: str = "mean", attention_mask: Optional[torch.Tensor] = None):
         """This rank's rows of the GLOBAL inputs [n, ...].  Returns (lo, hi, pooled float32 [L, hi-lo, D] or None when the
-        shard is empty, actions float64 [hi-lo, A])."""
+        shard is empty, actions float64 [hi-lo, A]).  `attention_mask` [n, P] marks right-padded (ragged) prompts; each
+        micro-batch is trimmed to its own longest row before it is sent to the device."""
         n = input_ids.shape[0]
         if pixel_values.shape[0] != n:
             raise ValueError("input_ids and pixel_values disagree on the number of observations")
@@ -63,9 +64,14 @@ class ShardedCollector:
         pooled, actions = [], []
         for s in range(lo, hi, self.micro_batch):
             e = min(s + self.micro_batch, hi)
+            ids_mb, kw = input_ids[s:e], {}
+            if attention_mask is not None:
+                m = attention_mask[s:e]
+                width = max(1, int((m != 0).sum(1).max()))
+                ids_mb, kw = ids_mb[:, :width], {"attention_mask": m[:, :width]}
             embeds, act = self.vla.predict_action_and_capture(
-                input_ids[s:e], unnorm_key=unnorm_key, layer_indices=layers, pooling_method=pooling_method,
-                pixel_values=pixel_values[s:e])
+                ids_mb, unnorm_key=unnorm_key, layer_indices=layers, pooling_method=pooling_method,
+                pixel_values=pixel_values[s:e], **kw)
             pooled.append(np.stack([np.asarray(embeds[l], dtype=np.float32).reshape(e - s, -1) for l in layers]))
             actions.append(np.asarray(act, dtype=np.float64).reshape(e - s, -1))
         if not pooled:
@@ -73,12 +79,14 @@ class ShardedCollector:
         return lo, hi, np.concatenate(pooled, 1), np.concatenate(actions, 0)
 
     def run(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, unnorm_key: Optional[str],
-            layer_indices: Sequence[int], pooling_method: str = "mean", gather: bool = False):
+            layer_indices: Sequence[int], pooling_method: str = "mean", gather: bool = False,
+            attention_mask: Optional[torch.Tensor] = None):
         """Shard, run, and (gather=True) assemble the global result on rank 0 in the original row order.
 
         Returns `(pooled [L, n, D], actions [n, A])` on rank 0 (and on every rank when world == 1); other ranks get
         `(None, None)` with gather=True, or their local `(lo, hi, pooled, actions)` tuple with gather=False."""
-        lo, hi, pooled, actions = self.run_local(input_ids, pixel_values, unnorm_key, layer_indices, pooling_method)
+        lo, hi, pooled, actions = self.run_local(input_ids, pixel_values, unnorm_key, layer_indices, pooling_method,
+                                                 attention_mask)
         if self.world == 1:
             return pooled, actions
         if not gather:

@@ -146,6 +146,13 @@ int ovla_decode_rope_attention(const void* qkv, long long qkv_ld, const void* co
   return decode_rope_attn_launch(qkv, qkv_ld, cos_dev, sin_dev, pos, kc, vc, B, H, head_dim, Tmax, out, o_ld,
                                  static_cast<cudaStream_t>(stream));
 }
+int ovla_decode_rope_attention_ragged(const void* qkv, long long qkv_ld, const void* cos_dev, const void* sin_dev, int pos,
+                                      const int* lens, int P, void* kc, void* vc, int B, int H, int head_dim, int Tmax,
+                                      void* out, long long o_ld, void* stream) {
+  if (!lens || P < 1) return set_error("ovla_decode_rope_attention_ragged: lens / P missing");
+  return decode_rope_attn_launch(qkv, qkv_ld, cos_dev, sin_dev, pos, kc, vc, B, H, head_dim, Tmax, out, o_ld,
+                                 static_cast<cudaStream_t>(stream), lens, P);
+}
 int ovla_rope_kv(void* qkv, int B, int T, int H, int head_dim, int pos0, const void* cos_dev, const void* sin_dev,
                  void* kc, void* vc, int Tmax, void* stream) {
   return rope_kv_launch(qkv, B, T, H, head_dim, pos0, cos_dev, sin_dev, kc, vc, Tmax, static_cast<cudaStream_t>(stream));
@@ -154,6 +161,13 @@ int ovla_pool_tokens(const void* x, long long batch_stride, long long ld, int B,
                      float* out, long long out_batch_stride, void* stream) {
   return pool_tokens_launch(x, batch_stride, ld, B, n_rows, D, mode, out, out_batch_stride,
                             static_cast<cudaStream_t>(stream));
+}
+int ovla_pool_tokens_ragged(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
+                            const int* lens, int P, float* out, long long out_batch_stride, void* stream) {
+  if (!lens || P < 1) return set_error("ovla_pool_tokens_ragged: lens / P missing");
+  if (n_rows - (P - 1) < 1) return set_error("ovla_pool_tokens_ragged: a row of length 1 would pool nothing");
+  return pool_tokens_launch(x, batch_stride, ld, B, n_rows, D, mode, out, out_batch_stride,
+                            static_cast<cudaStream_t>(stream), lens, P);
 }
 int ovla_argmax(const float* logits, long long ld, int rows, int n, long long* out, void* stream) {
   return argmax_launch(logits, ld, rows, n, out, static_cast<cudaStream_t>(stream));

@@ -28,7 +28,10 @@ __device__ __forceinline__ void dec_sync() {
 }
 
 // dyn: max(ctx, kDecGroups * HD) floats, sq: HD floats, red: kDecThreads / 32 floats (all shared memory)
-template <int HD, bool LDCG, bool NAMED_BAR = false>
+// FAST: short contexts issue all their K (then V) loads up front -- the latency-bound small-batch form; it holds
+// kDecFast * kDecR 16-byte registers per lane, which costs occupancy the HBM-bound large-batch launch needs (bs = 256:
+// 43 -> 65 ms per step with it), so the per-layer kernel instantiates both and picks by grid size.  Same bits either way.
+template <int HD, bool LDCG, bool NAMED_BAR = false, bool FAST = true>
 __device__ __forceinline__ void decode_rope_attn_body(const __nv_bfloat16* __restrict__ row, long long D,
                                                       const __nv_bfloat16* __restrict__ cos_t,
                                                       const __nv_bfloat16* __restrict__ sin_t, int pos,
@@ -64,7 +67,7 @@ __device__ __forceinline__ void decode_rope_attn_body(const __nv_bfloat16* __res
   // ALL their K loads up front and all their V loads before the softmax, so the phase is two memory round trips plus
   // the block reductions instead of ~10 dependent rounds; longer contexts loop.  Same arithmetic in both forms.
   constexpr int kStep = kDecGroups * kDecR;
-  const bool fast = ctx <= kDecFast * kStep;
+  const bool fast = FAST && ctx <= kDecFast * kStep;
   auto score_block = [&](int base, const uint4* u) {
     const int j0 = base + grp * kDecR;
 #pragma unroll
@@ -89,18 +92,19 @@ __device__ __forceinline__ void decode_rope_attn_body(const __nv_bfloat16* __res
       u[r] = *reinterpret_cast<const uint4*>(base_ptr + static_cast<long long>(j) * HD + hl * 8);
     }
   };
-  uint4 uf[kDecFast][kDecR];
+  constexpr int kF = FAST ? kDecFast : 1;
+  uint4 uf[kF][kDecR];
   // ---- scores: 16 lanes per key, kDecR keys per group per block
   // (trip counts are block-uniform: both 16-lane halves of a warp must reach the shuffles together)
   if (fast) {
 #pragma unroll
-    for (int it = 0; it < kDecFast; ++it) load_block(kb, it * kStep, uf[it]);
+    for (int it = 0; it < kF; ++it) load_block(kb, it * kStep, uf[it]);
 #pragma unroll
-    for (int it = 0; it < kDecFast; ++it)
+    for (int it = 0; it < kF; ++it)
       if (it * kStep < ctx) score_block(it * kStep, uf[it]);
     // V rows on their way while the softmax runs
 #pragma unroll
-    for (int it = 0; it < kDecFast; ++it) load_block(vb, it * kStep, uf[it]);
+    for (int it = 0; it < kF; ++it) load_block(vb, it * kStep, uf[it]);
   } else {
     for (int base = 0; base < ctx; base += kStep) {
       uint4 u[kDecR];
@@ -157,7 +161,7 @@ __device__ __forceinline__ void decode_rope_attn_body(const __nv_bfloat16* __res
   };
   if (fast) {
 #pragma unroll
-    for (int it = 0; it < kDecFast; ++it)
+    for (int it = 0; it < kF; ++it)
       if (it * kStep < ctx) pv_block(it * kStep, uf[it]);
   } else {
     for (int base = 0; base < ctx; base += kStep) {

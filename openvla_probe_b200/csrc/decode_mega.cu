@@ -373,6 +373,8 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
 
   const int H = a.H;
   const float scale = a.attn_scale;
+  // ragged (right-padded) prompts: row b sits (P - lens[b]) positions before the longest row
+  auto row_pos = [&](int b) { return a.lens ? max(0, a.pos - (a.P - min(max(a.lens[b], 1), a.P))) : a.pos; };
   // optional timeline (OVLA_MEGA_TRACE): CTA 0 and the last CTA stamp %globaltimer at every phase edge
   unsigned long long* tr = nullptr;
   int tr_n = 0;
@@ -392,7 +394,8 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
         const int b = p / H, h = p - b * H;
         const long long head_off = (static_cast<long long>(b) * H + h) * a.Tmax * 128;
         const __nv_bfloat16* base = a.kv + layer * a.kv_layer_elems + (threadIdx.x ? a.kv_layer_elems / 2 : 0) + head_off;
-        if (a.pos > 0) l2_prefetch_bulk(base, static_cast<uint32_t>(a.pos) * 128u * 2u);
+        const int pos_b = row_pos(b);
+        if (pos_b > 0) l2_prefetch_bulk(base, static_cast<uint32_t>(pos_b) * 128u * 2u);
       }
     }
     // [norm1 + QKV]
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
     for (int p = blockIdx.x; p < ((a.dbg & 2) ? 0 : a.M * H); p += gridDim.x) {
       const int b = p / H, h = p - b * H;
       const long long head_off = (static_cast<long long>(b) * H + h) * a.Tmax * 128;
-      decode_rope_attn_body<128, true, true>(a.qkv + b * 3LL * D + h * 128, D, a.rope_cos, a.rope_sin, a.pos,
+      decode_rope_attn_body<128, true, true>(a.qkv + b * 3LL * D + h * 128, D, a.rope_cos, a.rope_sin, row_pos(b),
                                        a.kv + layer * a.kv_layer_elems + head_off,
                                        a.kv + layer * a.kv_layer_elems + a.kv_layer_elems / 2 + head_off,
                                        a.attn + b * static_cast<long long>(D) + h * 128, scale, dyn, s_sq, s_red);

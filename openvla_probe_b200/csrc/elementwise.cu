@@ -116,6 +116,38 @@ int copy_rows_launch(const void* src, long long src_batch, long long src_ld, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------- ragged prompts
+// out[b, :] = x[b, last - (P - lens[b]), :]: the last real position of every right-padded row (lm_head input of the
+// first generated token).  Also validates the lengths (err flag 2 for a length outside [1, P]).
+__global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, long long batch_stride, long long ld, int last,
+                                        const int* __restrict__ lens, int P, int D, __nv_bfloat16* __restrict__ out,
+                                        int* __restrict__ err) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= D) return;
+  int len = lens[b];
+  if (len < 1 || len > P) {
+    if (c == 0) atomicExch(err, 2);
+    len = min(max(len, 1), P);
+  }
+  const long long r = last - (P - len);
+  *reinterpret_cast<uint4*>(out + static_cast<long long>(b) * D + c) =
+      *reinterpret_cast<const uint4*>(x + b * batch_stride + r * ld + c);
+}
+
+int gather_last_rows_launch(const void* x, long long batch_stride, long long ld, int last, const int* lens, int P, int B,
+                            int D, void* out, int* err_flag, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (D % 8) return set_error("gather_last_rows: D must be a multiple of 8");
+  if (last - (P - 1) < 0) return set_error("gather_last_rows: shortest possible row starts before the buffer");
+  dim3 grid((D / 8 + 127) / 128, B);
+  gather_last_rows_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(x), batch_stride, ld, last, lens, P, D,
+                                               static_cast<__nv_bfloat16*>(out), err_flag);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- embed + splice
 // x[b, 0] = E[ids[b,0]];  x[b, 1..np] = proj[b, :];  x[b, np+j] = E[ids[b,j]], j >= 1
 // (modeling_prismatic.py:380-385: [BOS | projected patches | text[1:]])
@@ -231,11 +263,16 @@ int rope_kv_launch(void* qkv, int B, int T, int H, int hd, int pos0, const void*
 // experiments/robot/openvla_utils.py:126-131,193-199:  hs.float().mean(1)  or  hs[:, -1]  per layer.
 // x [B, T(ld rows), D] bf16 -> out [B, D] fp32.  mode 0: mean over rows [0, n_rows); mode 1: row n_rows-1.
 // CTA = 8 warps over 256 columns; warp w sums rows w, w+8, ... with 16-byte loads; smem tree over warps.
+// Ragged (right-padded) prompts: `lens` (int32 [B], may be null) holds each row's true prompt length out of `P`; row b
+// then pools over its own n_rows - (P - lens[b]) leading rows, in the same summation order as a uniform batch of that
+// length.
 __global__ void __launch_bounds__(256) pool_tokens_kernel(const __nv_bfloat16* __restrict__ x, long long batch_stride,
                                                           long long ld, int n_rows, int D, int mode,
-                                                          float* __restrict__ out, long long out_batch_stride) {
+                                                          float* __restrict__ out, long long out_batch_stride,
+                                                          const int* __restrict__ lens, int P) {
   __shared__ float red[8][256];
   const int b = blockIdx.y;
+  if (lens) n_rows = max(1, n_rows - (P - min(max(lens[b], 1), P)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -279,14 +316,14 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const __nv_bfloat16* _
 }
 
 int pool_tokens_launch(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
-                       float* out, long long out_batch_stride, cudaStream_t st) {
+                       float* out, long long out_batch_stride, cudaStream_t st, const int* lens, int P) {
   if (B <= 0) return 0;
   if (n_rows <= 0) return set_error("pool_tokens: empty token range");
   if (D % 8) return set_error("pool_tokens: D must be a multiple of 8");
   dim3 grid((D + 255) / 256, B);
   ProfScope prof(kCatPool, 0.0, (mode == 0 ? 2.0 * B * n_rows * D : 2.0 * B * D) + 4.0 * B * D, st);
   pool_tokens_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), batch_stride, ld, n_rows, D, mode,
-                                          out, out_batch_stride);
+                                          out, out_batch_stride, lens, P);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;

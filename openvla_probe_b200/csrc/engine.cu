@@ -114,6 +114,7 @@ struct OvlaEngine {
   long long graph_replays = 0;  // cudaGraphLaunch calls made by ovla_run (tests assert that a replay happened)
   // staging for ovla_run_host
   long long* in_ids = nullptr;
+  int* in_lens = nullptr;
   bf16* in_px = nullptr;
   long long* out_tokens = nullptr;
   int max_P = 0;
@@ -280,6 +281,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   }
   e->max_P = static_cast<int>(T - e->np);
   W(&e->in_ids, B * std::max(1, e->max_P));
+  W(&e->in_lens, B);
   W(&e->in_px, B * 3LL * d.n_towers * d.image_size * d.image_size);
   W(&e->out_tokens, 64LL * B);
   if (!rc) rc = cudaMemset(e->err_flag, 0, 16) == cudaSuccess ? 0 : set_error("memset");
@@ -596,7 +598,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
     LayerW& l = e->layers[i];
     if (a->pool_len > 0)
       OVLA_TRY(pool_tokens_launch(e->l_x, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
-                                  e->pooled + 1LL * i * B * D, D, st));
+                                  e->pooled + 1LL * i * B * D, D, st, a->prompt_lens_dev, a->P));
     if (a->pool_len > 0) OVLA_TRY(pooled_to_host(e, i, B, st));
     if (a->hidden_out_dev)
       CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
@@ -634,7 +636,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
   OVLA_TRY(rmsnorm_launch(e->l_x, D, e->final_norm.ptr, d.rms_eps, e->l_h, D, rows, D, st));
   if (a->pool_len > 0)
     OVLA_TRY(pool_tokens_launch(e->l_h, 1LL * T * D, D, B, a->pool_len, D, a->pool_mode,
-                                e->pooled + 1LL * d.llm_layers * B * D, D, st));
+                                e->pooled + 1LL * d.llm_layers * B * D, D, st, a->prompt_lens_dev, a->P));
   if (a->pool_len > 0) OVLA_TRY(pooled_to_host(e, d.llm_layers, B, st));
   if (a->hidden_out_dev)
     CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * d.llm_layers * rows * D, e->l_h,
@@ -646,7 +648,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
 // RoPE + KV append + attention, o_proj(+res), RMSNorm, gate/up SwiGLU, down(+res)); for B <= 8 the linears are
 // weight-streaming GEMVs chained with programmatic dependent launch.  Ends with final norm + lm_head (fp32 storage of
 // bf16-rounded logits, as HF's `.float()`).
-int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t st) {
+int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, const int* lens, int P, cudaStream_t st) {
   const OvlaDims& d = e->d;
   const int D = d.llm_dim, H = d.llm_heads, hd = e->head_dim;
   const int Tmax = d.max_seq;
@@ -663,6 +665,7 @@ int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t s
     { static const int dbg = getenv("OVLA_MEGA_DBG") ? atoi(getenv("OVLA_MEGA_DBG")) : 0; a.dbg = dbg; }
     a.n_layers = d.llm_layers; a.M = B; a.D = D; a.I = d.llm_inter; a.H = H; a.head_dim = hd; a.vocab = d.vocab;
     a.Tmax = Tmax; a.pos = pos; a.eps = d.rms_eps;
+    a.lens = lens; a.P = P;
     const int rc = decode_step_launch(a, st);
     if (rc != -2) return rc;
   }
@@ -671,7 +674,7 @@ int run_decode_step(OvlaEngine* e, int B, int pos, float* logits, cudaStream_t s
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, B, D, st));
     OVLA_TRY(linear(e, e->l_h, D, l.qkv_w, B, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
     OVLA_TRY(decode_rope_attn_launch(e->l_qkv, 3LL * D, e->rope_cos.ptr, e->rope_sin.ptr, pos, e->k_cache(i),
-                                     e->v_cache(i), B, H, hd, Tmax, e->l_attn, D, st));
+                                     e->v_cache(i), B, H, hd, Tmax, e->l_attn, D, st, lens, P));
     OVLA_TRY(linear(e, e->l_attn, D, l.o_w, B, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, B, D, st));
     OVLA_TRY(linear(e, e->l_h, D, l.gate_up_w, B, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0, 0,
@@ -699,6 +702,8 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     return set_error("ovla_run: sequence %d + %d new tokens exceeds max_seq %d", T, n_new, d.max_seq);
   if (a->pool_len < 0 || a->pool_len > T) return set_error("ovla_run: pool_len %d out of range (T=%d)", a->pool_len, T);
   if (!a->input_ids_dev || !a->pixel_values_dev) return set_error("ovla_run: null input");
+  if (a->prompt_lens_dev && a->pool_len > 0 && a->pool_len - (P - 1) < 1)
+    return set_error("ovla_run: pool_len %d leaves nothing to pool for a row of length 1 (P=%d)", a->pool_len, P);
   // The KV cache is laid out for the live batch: [B, H, max_seq, hd] per layer half (capacity max_batch).
 
   // ---- vision towers + projector
@@ -749,12 +754,19 @@ static int run_impl(OvlaEngine* e, const OvlaRunArgs* a, cudaStream_t st) {
     float* lg = a->step_logits_out_dev ? a->step_logits_out_dev + 1LL * s * B * d.vocab : e->logits;
     if (s == 0) {
       // HF: logits = lm_head(h) in bf16, then .float()  => fp32 storage of bf16-rounded values
-      OVLA_TRY(linear(e, e->l_h + 1LL * (T - 1) * D, 1LL * T * D, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr,
-                      nullptr, 0, 0, 1, st));
+      const bf16* last = e->l_h + 1LL * (T - 1) * D;
+      long long ld_last = 1LL * T * D;
+      if (a->prompt_lens_dev) {  // ragged: each row's own last real position, gathered into a dense [B, D] block
+        OVLA_TRY(gather_last_rows_launch(e->l_h, 1LL * T * D, D, T - 1, a->prompt_lens_dev, P, B, D, e->l_attn,
+                                         e->err_flag, st));
+        last = e->l_attn;
+        ld_last = D;
+      }
+      OVLA_TRY(linear(e, last, ld_last, e->lm_head, B, kModeF32, lg, d.vocab, nullptr, nullptr, nullptr, 0, 0, 1, st));
     } else {
       OVLA_TRY(embed_splice_launch(e->tokens + 1LL * (s - 1) * B, B, 1, e->embed.ptr, d.vocab, nullptr, 0, D, e->l_x,
                                    e->err_flag, st));
-      OVLA_TRY(run_decode_step(e, B, T + s - 1, lg, st));
+      OVLA_TRY(run_decode_step(e, B, T + s - 1, lg, a->prompt_lens_dev, P, st));
     }
     OVLA_TRY(argmax_launch(lg, d.vocab, B, d.vocab, e->tokens + 1LL * s * B, st));
   }
@@ -786,7 +798,7 @@ extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
   key.a.n_new_tokens = a->n_new_tokens; key.a.pooled_out_dev = a->pooled_out_dev;
   key.a.tokens_out_dev = a->tokens_out_dev; key.a.step_logits_out_dev = a->step_logits_out_dev;
   key.a.hidden_out_dev = a->hidden_out_dev; key.a.projector_out_dev = a->projector_out_dev;
-  key.a.patches_out_dev = a->patches_out_dev;
+  key.a.patches_out_dev = a->patches_out_dev; key.a.prompt_lens_dev = a->prompt_lens_dev;
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     if (e->graphs.size() >= 16) {  // bounded cache: drop everything (keys are few in steady state)
@@ -838,7 +850,8 @@ extern "C" int ovla_run(OvlaEngine* e, const OvlaRunArgs* a, void* stream) {
 }
 
 extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const void* px_host, int B, int P, int pool_len,
-                             int pool_mode, int n_new, float* pooled_host, long long* tokens_host, void* stream) {
+                             int pool_mode, int n_new, float* pooled_host, long long* tokens_host, const int* lens_host,
+                             void* stream) {
   if (!e) return set_error("ovla_run_host: null engine");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(e->device));
@@ -851,6 +864,13 @@ extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const voi
   CUDA_TRY(cudaMemcpyAsync(e->in_ids, ids_host, sizeof(long long) * B * P, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(e->in_px, px_host, sizeof(bf16) * px_elems, cudaMemcpyHostToDevice, st));
   OvlaRunArgs a = {};
+  if (lens_host) {
+    for (int b = 0; b < B; ++b)
+      if (lens_host[b] < 1 || lens_host[b] > P)
+        return set_error("ovla_run_host: prompt length %d of row %d outside [1, %d]", lens_host[b], b, P);
+    CUDA_TRY(cudaMemcpyAsync(e->in_lens, lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    a.prompt_lens_dev = e->in_lens;
+  }
   a.input_ids_dev = e->in_ids;
   a.pixel_values_dev = e->in_px;
   a.B = B;
@@ -894,6 +914,7 @@ extern "C" int ovla_run_host(OvlaEngine* e, const long long* ids_host, const voi
   CUDA_TRY(cudaStreamSynchronize(st));
   if (err) {
     cudaMemset(e->err_flag, 0, sizeof(int));
+    if (err == 2) return set_error("ovla_run_host: a prompt length lies outside [1, %d]", P);
     return set_error("ovla_run_host: input_ids contain a token id outside [0, %d)", d.vocab);
   }
   return 0;

@@ -40,6 +40,8 @@ struct DecodeStepArgs {
   float* logits;                        // [M, vocab] fp32
   unsigned* barrier;                    // one counter, zeroed by the launcher
   int n_layers, M, D, I, H, head_dim, vocab, Tmax, pos;
+  const int* lens;                      // ragged prompts: int32 [M] true prompt lengths out of P (row m decodes at
+  int P;                                // pos - (P - lens[m])); null = every row at `pos`
   float eps;
   unsigned long long* trace;            // optional timeline buffer [2][trace_stride] (debug), else null
   int trace_stride;
@@ -55,7 +57,7 @@ int gemv_launch(const void* x, long long ldx, const void* W, long long ldw, int 
 // decode.cu -- fused RoPE + KV append + single-query attention
 int decode_rope_attn_launch(const void* qkv, long long qkv_ld, const void* cos_t, const void* sin_t, int pos, void* kc,
                             void* vc, int B, int H, int head_dim, int Tmax, void* out, long long o_ld,
-                            cudaStream_t st);
+                            cudaStream_t st, const int* lens = nullptr, int P = 0);
 
 // norm.cu
 int layernorm_launch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
@@ -87,7 +89,10 @@ int embed_splice_launch(const void* ids, int B, int P, const void* E, int vocab,
 int rope_kv_launch(void* qkv, int B, int T, int H, int hd, int pos0, const void* cos_t, const void* sin_t, void* kc,
                    void* vc, int Tmax, cudaStream_t st);
 int pool_tokens_launch(const void* x, long long batch_stride, long long ld, int B, int n_rows, int D, int mode,
-                       float* out, long long out_batch_stride, cudaStream_t st);
+                       float* out, long long out_batch_stride, cudaStream_t st, const int* lens = nullptr, int P = 0);
+// out[b, :] = x[b, last - (P - lens[b]), :]  (the last real position of each right-padded row)
+int gather_last_rows_launch(const void* x, long long batch_stride, long long ld, int last, const int* lens, int P, int B,
+                            int D, void* out, int* err_flag, cudaStream_t st);
 int argmax_launch(const float* x, long long ld, int rows, int n, long long* out, cudaStream_t st);
 int detok_unnorm_launch(const long long* ids, int n, int action_dim, int vocab_size, const double* centers,
                         int n_centers, const double* q01, const double* q99, const unsigned char* mask, double* out,

@@ -29,6 +29,7 @@ class _RunArgs(C.Structure):
         ("B", C.c_int), ("P", C.c_int), ("pool_len", C.c_int), ("pool_mode", C.c_int), ("n_new_tokens", C.c_int),
         ("pooled_out_dev", C.c_void_p), ("tokens_out_dev", C.c_void_p), ("step_logits_out_dev", C.c_void_p),
         ("hidden_out_dev", C.c_void_p), ("projector_out_dev", C.c_void_p), ("patches_out_dev", C.c_void_p),
+        ("prompt_lens_dev", C.c_void_p),
     ]
 
 
@@ -99,8 +100,9 @@ class Engine:
     # ------------------------------------------------------------------ run
     def run(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, pool_len: int = 0, pool_mode: int = 0,
             n_new_tokens: int = 0, want_hidden: bool = False, want_logits: bool = False, want_projector: bool = False,
-            want_patches: bool = False):
-        """Device-resident entry (ovla_run).  Returns a dict of device tensors."""
+            want_patches: bool = False, prompt_lens: Optional[torch.Tensor] = None):
+        """Device-resident entry (ovla_run).  Returns a dict of device tensors.  `prompt_lens` (int32 [B], optional):
+        true lengths of right-padded rows of `input_ids` (OvlaRunArgs.prompt_lens_dev)."""
         if not self._finalized:
             raise _lib.OvlaError("engine weights are not bound (call load_state_dict / finalize)")
         cfg, tc = self.config, self.config.text_config
@@ -113,6 +115,13 @@ class Engine:
         a = _RunArgs()
         a.input_ids_dev, a.pixel_values_dev = ids.data_ptr(), px.data_ptr()
         a.B, a.P, a.pool_len, a.pool_mode, a.n_new_tokens = B, P, pool_len, pool_mode, n_new_tokens
+        if prompt_lens is not None:
+            if prompt_lens.numel() != B:
+                raise ValueError("prompt_lens must hold one length per row")
+            lens = prompt_lens.to(self.device, torch.int32).contiguous()
+            if B and (int(lens.min()) < 1 or int(lens.max()) > P):
+                raise ValueError(f"prompt lengths must lie in [1, {P}]")
+            a.prompt_lens_dev = lens.data_ptr()
         if pool_len > 0:
             out["pooled"] = torch.empty(L + 1, B, D, dtype=torch.float32, device=self.device)
             a.pooled_out_dev = out["pooled"].data_ptr()
@@ -136,18 +145,22 @@ class Engine:
         return out
 
     def run_host(self, input_ids_host: torch.Tensor, pixel_values_host: torch.Tensor, pool_len: int, pool_mode: int,
-                 n_new_tokens: int, pooled_out_host: Optional[torch.Tensor], tokens_out_host: Optional[torch.Tensor]):
+                 n_new_tokens: int, pooled_out_host: Optional[torch.Tensor], tokens_out_host: Optional[torch.Tensor],
+                 prompt_lens_host: Optional[torch.Tensor] = None):
         """Host-buffer entry (ovla_run_host): H2D copies, fused pass, D2H copies, stream sync -- all inside the call."""
         if not self._finalized:
             raise _lib.OvlaError("engine weights are not bound (call load_state_dict / finalize)")
         B, P = input_ids_host.shape
         assert input_ids_host.dtype == torch.int64 and input_ids_host.is_contiguous() and not input_ids_host.is_cuda
         assert pixel_values_host.dtype == torch.bfloat16 and pixel_values_host.is_contiguous()
+        if prompt_lens_host is not None:
+            assert prompt_lens_host.dtype == torch.int32 and prompt_lens_host.is_contiguous() and prompt_lens_host.numel() == B
         _lib.check(self.lib.ovla_run_host(
             self._h, C.c_void_p(input_ids_host.data_ptr()), C.c_void_p(pixel_values_host.data_ptr()), B, P,
             pool_len, pool_mode, n_new_tokens,
             C.c_void_p(pooled_out_host.data_ptr()) if pooled_out_host is not None else None,
             C.c_void_p(tokens_out_host.data_ptr()) if tokens_out_host is not None else None,
+            C.c_void_p(prompt_lens_host.data_ptr()) if prompt_lens_host is not None else None,
             _lib.stream_ptr()))
 
     def set_option(self, name: str, value: int) -> None:

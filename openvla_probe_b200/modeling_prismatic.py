@@ -7,6 +7,10 @@ behaviour, but every tensor op runs in libovla_b200.so (hand-written sm_100a ker
 Differences that are deliberate and documented in DESIGN.md:
   * `predict_action` accepts B >= 1 (the reference's generation path is batch-1 only, modeling_prismatic.py:326,460-463);
     row b of the result equals the reference's B == 1 result for observation b; shape (7,) for B == 1, (B, 7) otherwise.
+  * Ragged batches: prompts of different lengths are passed RIGHT-padded with an `attention_mask` of ones followed by
+    zeros (the tokenizer's `padding_side="right"`, processing_prismatic.py; the reference splices that mask at
+    modeling_prismatic.py:388-390).  Row b then behaves as its own batch-1 call: 29871 goes right after its last real
+    token, the capture pools over its true length and it decodes at its own positions.
   * `predict_action_and_capture` does the reference's two passes (`vla(**inputs, output_hidden_states=True)` then
     `vla.predict_action(**inputs)`, experiments/robot/openvla_utils.py:188-203) in ONE prefill: LLM attention is
     causal, so hidden states at positions [0, T-1) of the predict pass (which appends token 29871) are those of the
@@ -91,12 +95,24 @@ class OpenVLAForActionPrediction:
         unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
         return self.norm_stats[unnorm_key]["action"]
 
-    def _append_empty(self, input_ids: torch.Tensor) -> torch.Tensor:
-        """modeling_prismatic.py:512-515: batch-wide test, append 29871 unless every row already ends with it."""
-        if not torch.all(input_ids[:, -1] == EMPTY_TOKEN_ID):
-            pad = torch.full((input_ids.shape[0], 1), EMPTY_TOKEN_ID, dtype=input_ids.dtype, device=input_ids.device)
-            input_ids = torch.cat((input_ids, pad), dim=1)
-        return input_ids
+    def _append_empty(self, input_ids: torch.Tensor, lens: Optional[torch.Tensor] = None):
+        """modeling_prismatic.py:512-515: batch-wide test, append 29871 unless every row already ends with it.
+        Ragged rows (`lens` = true lengths, right-padded): the test looks at each row's last REAL token and 29871 goes
+        right behind it; returns (ids, lens) with the lengths counting the appended token."""
+        if lens is None:
+            if not torch.all(input_ids[:, -1] == EMPTY_TOKEN_ID):
+                pad = torch.full((input_ids.shape[0], 1), EMPTY_TOKEN_ID, dtype=input_ids.dtype, device=input_ids.device)
+                input_ids = torch.cat((input_ids, pad), dim=1)
+            return input_ids, None
+        lens = lens.to("cpu", torch.int64)                     # the lengths stay on the host
+        at = lens.to(input_ids.device)
+        rows = torch.arange(input_ids.shape[0], device=input_ids.device)
+        if torch.all(input_ids[rows, at - 1] == EMPTY_TOKEN_ID):
+            return input_ids, lens
+        pad = torch.full((input_ids.shape[0], 1), self.pad_token_id, dtype=input_ids.dtype, device=input_ids.device)
+        input_ids = torch.cat((input_ids, pad), dim=1)
+        input_ids[rows, at] = EMPTY_TOKEN_ID
+        return input_ids, lens + 1
 
     def _check_inputs(self, input_ids, pixel_values, attention_mask):
         if input_ids is None or pixel_values is None:
@@ -106,15 +122,23 @@ class OpenVLAForActionPrediction:
         if input_ids.shape[0] != pixel_values.shape[0]:
             # modeling_prismatic.py:418-419
             raise ValueError("Non-homogenous batch of (text, image) input -- forward() does not support mixed batches!")
+        lens = None
         if attention_mask is not None and not bool(torch.all(attention_mask != 0)):
-            raise ValueError("padded (ragged) prompts are not supported: every row must be a full-length prompt "
-                             "(the reference asserts batch size 1 here, modeling_prismatic.py:326)")
+            if tuple(attention_mask.shape) != tuple(input_ids.shape):
+                raise ValueError("`attention_mask` must have the shape of `input_ids`")
+            m = (attention_mask != 0).to(torch.int64).cpu()
+            lens = m.sum(1)
+            right_padded = bool(torch.all(m == (torch.arange(m.shape[1]).view(1, -1) < lens.view(-1, 1)).to(torch.int64)))
+            if not right_padded or int(lens.min()) < 1:
+                raise ValueError("ragged prompts must be RIGHT-padded (mask = ones then zeros, at least the BOS token per "
+                                 "row); left padding would shift the BOS / patch splice of modeling_prismatic.py:380-390")
         c = self.config
         want = (3 * len(c.towers), c.image_size, c.image_size)
         if tuple(pixel_values.shape[1:]) != want:
             raise ValueError(f"`pixel_values` must be [B, {want[0]}, {want[1]}, {want[2]}], got {tuple(pixel_values.shape)}")
+        return lens
 
-    def _finish_sequences(self, input_ids: torch.Tensor, new_tokens: np.ndarray, n: int) -> np.ndarray:
+    def _finish_sequences(self, input_ids: torch.Tensor, new_tokens: np.ndarray, n: int, lens=None) -> np.ndarray:
         """HF greedy `generate` stops a row at EOS; `generated_ids[0, -n:]` (modeling_prismatic.py:521) then reaches
         back into the prompt.  The engine always produces n tokens (greedy is deterministic, so the prefix up to the
         first EOS is what HF would have produced); the truncation is replayed here per row."""
@@ -125,7 +149,8 @@ class OpenVLAForActionPrediction:
             row = new_tokens[b]
             hit = np.nonzero(row == eos)[0]
             gen = row[: hit[0] + 1] if hit.size else row
-            seq = np.concatenate([ids_host[b], gen])
+            prompt = ids_host[b] if lens is None else ids_host[b, : int(lens[b])]
+            seq = np.concatenate([prompt, gen])
             out[b] = seq[-n:]
         return out
 
@@ -234,7 +259,7 @@ class OpenVLAForActionPrediction:
                  attention_mask=None, do_sample: bool = False, return_tokens: bool = False, pooled_out=None, **unused):
         if do_sample:
             raise ValueError("only greedy decoding (do_sample=False) is implemented, as used by the reference path")
-        self._check_inputs(input_ids, pixel_values, attention_mask)
+        lens0 = self._check_inputs(input_ids, pixel_values, attention_mask)
         n_act = self.get_action_dim(unnorm_key)
         B = input_ids.shape[0]
         if B == 0:
@@ -242,14 +267,16 @@ class OpenVLAForActionPrediction:
             return empty, np.zeros((self.config.text_config.num_hidden_layers + 1, 0,
                                     self.config.text_config.hidden_size), dtype=np.float32)
         P0 = input_ids.shape[1]
-        ids = self._append_empty(input_ids)
+        ids, lens = self._append_empty(input_ids, lens0)
         P = ids.shape[1]
-        # capture pass of the reference sees the prompt as given (P0 tokens): pool over [0, n_patches + P0)
+        lens32 = lens.to(torch.int32).contiguous() if lens is not None else None
+        # capture pass of the reference sees the prompt as given (P0 tokens): pool over [0, n_patches + P0); a ragged row
+        # pools over its own n_patches + len0_b rows (the engine subtracts P - len_b = P0 - len0_b from pool_len per row)
         pool_len = self.config.n_patches + P0 if capture else 0
         pool_mode = 0 if pooling_method == "mean" else 1
         tc = self.config.text_config
         if ids.is_cuda or pixel_values.is_cuda:
-            r = self.engine.run(ids, pixel_values, pool_len, pool_mode, n_act)
+            r = self.engine.run(ids, pixel_values, pool_len, pool_mode, n_act, prompt_lens=lens32)
             tokens = r["tokens"].cpu().numpy()
             pooled = r["pooled"].cpu().numpy() if capture else None
         else:
@@ -271,7 +298,7 @@ class OpenVLAForActionPrediction:
                 pool_p = pooled_out
             else:
                 pool_p = self._pinned("pool", pool_shape, torch.float32) if capture else None
-            self.engine.run_host(ids_p, px_p, pool_len, pool_mode, n_act, pool_p, tok_p)
+            self.engine.run_host(ids_p, px_p, pool_len, pool_mode, n_act, pool_p, tok_p, lens32)
             tokens = tok_p.numpy().copy()
             if not capture:
                 pooled = None
@@ -279,7 +306,7 @@ class OpenVLAForActionPrediction:
                 pooled = pool_p.numpy()               # the caller's buffer: views, no copy
             else:
                 pooled = torch.empty(pool_shape, dtype=torch.float32).copy_(pool_p).numpy()   # threaded copy out of staging
-        final_ids = self._finish_sequences(ids, tokens, n_act)
+        final_ids = self._finish_sequences(ids, tokens, n_act, lens)
         actions = self._detokenize(final_ids, unnorm_key)
         if B == 1:
             actions = actions[0]                      # reference returns shape (action_dim,) (robot_utils.py:78)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ovla_b200.h but not exported by libovla_b200.so"
-    assert lib.ovla_abi_version() == 1
+    assert lib.ovla_abi_version() == 2
 
 
 def test_every_entry_point_has_header_derived_argtypes(lib):
@@ -87,6 +87,7 @@ def _bare_model():
     m = object.__new__(OpenVLAForActionPrediction)
     m.config = dataclasses.replace(config.tiny(), norm_stats=stats)
     m.norm_stats = stats
+    m.pad_token_id = m.config.pad_token_id
     return m
 
 
@@ -103,10 +104,30 @@ def test_unnorm_key_conventions():
 def test_append_29871_is_batch_wide():
     m = _bare_model()
     ids = torch.tensor([[1, 5, 29871], [1, 6, 29871]])
-    assert m._append_empty(ids).shape == (2, 3)
+    assert m._append_empty(ids)[0].shape == (2, 3)
     ids[0, -1] = 9
-    out = m._append_empty(ids)
-    assert out.shape == (2, 4) and out[:, -1].tolist() == [29871, 29871]
+    out, lens = m._append_empty(ids)
+    assert lens is None and out.shape == (2, 4) and out[:, -1].tolist() == [29871, 29871]
+
+
+def test_append_29871_ragged_rows_get_it_behind_their_last_real_token():
+    """Right-padded rows: the batch-wide test of modeling_prismatic.py:512 looks at each row's last real token, 29871
+    lands right behind it and the lengths count it."""
+    m = _bare_model()
+    pad = m.pad_token_id
+    ids = torch.tensor([[1, 5, 6, 7], [1, 8, pad, pad]])
+    out, lens = m._append_empty(ids, torch.tensor([4, 2]))
+    assert lens.tolist() == [5, 3]
+    assert out.tolist() == [[1, 5, 6, 7, 29871], [1, 8, 29871, pad, pad]]
+    # every row already ends with 29871 (before its pads): nothing appended
+    ids = torch.tensor([[1, 5, 6, 29871], [1, 29871, pad, pad]])
+    out, lens = m._append_empty(ids, torch.tensor([4, 2]))
+    assert out.shape == (2, 4) and lens.tolist() == [4, 2]
+    # the EOS replay reaches back into the row's REAL prompt, not into the pads
+    ids = torch.tensor([[1, 5, 6, 7, 29871], [1, 8, 29871, pad, pad]])
+    toks = np.array([[9, 2, 4, 4, 4, 4, 4], [9, 9, 9, 9, 9, 9, 3]])
+    got = m._finish_sequences(ids, toks, 7, lens=torch.tensor([5, 3]))
+    assert got[0].tolist() == [1, 5, 6, 7, 29871, 9, 2] and got[1].tolist() == toks[1].tolist()
 
 
 def test_eos_replay_matches_hf_semantics():
@@ -129,9 +150,17 @@ def test_input_validation_errors():
         m._check_inputs(ids, px[:, :3], None)
     mask = torch.ones(2, 5, dtype=torch.long)
     mask[1, -1] = 0
+    assert m._check_inputs(ids, px, mask).tolist() == [5, 4]          # right-padded: the rows' true lengths
+    assert m._check_inputs(ids, px, torch.ones(2, 5)) is None
+    mask[1] = torch.tensor([0, 1, 1, 1, 1])                           # left padding is rejected
     with pytest.raises(ValueError):
         m._check_inputs(ids, px, mask)
-    m._check_inputs(ids, px, torch.ones(2, 5))
+    mask[1] = torch.tensor([1, 0, 1, 1, 1])                           # holes are rejected
+    with pytest.raises(ValueError):
+        m._check_inputs(ids, px, mask)
+    mask[1] = 0                                                       # an empty row is rejected
+    with pytest.raises(ValueError):
+        m._check_inputs(ids, px, mask)
 
 
 def test_state_dict_schema_matches_oracle_and_golden():

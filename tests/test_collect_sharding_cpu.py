@@ -60,6 +60,24 @@ def test_single_process_micro_batches():
     assert all(np.array_equal(d[l], want_e[l]) for l in LAYERS)
 
 
+def test_ragged_micro_batches_are_trimmed_to_their_longest_row():
+    """attention_mask of right-padded prompts travels with the rows and every micro-batch is cut to its own width."""
+    ids, px = _inputs(7)
+    lens = [6, 2, 3, 1, 4, 4, 5]
+    mask = (torch.arange(6)[None] < torch.tensor(lens)[:, None]).long()
+
+    class Rec(FakeVLA):
+        def predict_action_and_capture(self, input_ids, attention_mask=None, **kw):
+            self.seen = getattr(self, "seen", []) + [(tuple(input_ids.shape), attention_mask.sum(1).tolist())]
+            return super().predict_action_and_capture(input_ids * attention_mask, **kw)
+
+    vla = Rec()
+    pooled, actions = ShardedCollector(vla, micro_batch=3).run(ids, px, "k", LAYERS, attention_mask=mask)
+    assert vla.seen == [((3, 6), [6, 2, 3]), ((3, 4), [1, 4, 4]), ((1, 5), [5])]
+    _, want_a = FakeVLA().predict_action_and_capture(ids * mask, layer_indices=LAYERS, pixel_values=px)
+    assert np.array_equal(actions, want_a)
+
+
 def _worker(rank, world, port, n, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -537,3 +537,64 @@ def test_center_crop_frames_bit_exact(L, B, H, W, scale):
     if scale == 1.0 and (H, W) == (224, 224):
         assert np.array_equal(ref, img)                                           # full box at native size is the identity
 
+
+
+# ----------------------------------------------------------------------------------------------- ragged prompts
+def test_pool_tokens_ragged_rows_equal_uniform_calls():
+    """ovla_pool_tokens_ragged: row b pools over n_rows - (P - lens[b]) rows, bit-identical to a uniform call of that
+    length (pool over each sample's true length)."""
+    import ctypes as C
+
+    from openvla_probe_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(0)
+    B, T, D, P, n_rows = 5, 40, 512, 9, 38
+    x = torch.randn(B, T, D, device="cuda").to(torch.bfloat16)
+    lens = torch.tensor([9, 1, 4, 9, 7], dtype=torch.int32, device="cuda")
+    for mode in (0, 1):
+        out = torch.empty(B, D, device="cuda")
+        _lib.check(lib.ovla_pool_tokens_ragged(x.data_ptr(), T * D, D, B, n_rows, D, mode, lens.data_ptr(), P,
+                                               out.data_ptr(), D, _lib.stream_ptr()))
+        for b in range(B):
+            nb = n_rows - (P - int(lens[b]))
+            one = torch.empty(1, D, device="cuda")
+            _lib.check(lib.ovla_pool_tokens(x[b].data_ptr(), T * D, D, 1, nb, D, mode, one.data_ptr(), D, _lib.stream_ptr()))
+            assert torch.equal(out[b], one[0]), (mode, b)
+            ref = x[b, :nb].float().mean(0) if mode == 0 else x[b, nb - 1].float()
+            assert torch.allclose(out[b], ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B", [3, 200])
+def test_decode_attention_ragged_rows_equal_uniform_calls(B):
+    """ovla_decode_rope_attention_ragged: row b works at pos - (P - lens[b]); output and the appended K/V rows are
+    bit-identical to a batch-1 call at that position (B = 200 takes the low-register looped form of the kernel, B = 3
+    the loads-up-front form: same bits)."""
+    from openvla_probe_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(1)
+    H, hd, Tmax, P, pos = 4, 128, 64, 10, 40
+    g = torch.Generator().manual_seed(2)
+    lens = torch.randint(1, P + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = P
+    qkv = torch.randn(B, 3 * H * hd, device="cuda").to(torch.bfloat16)
+    kc0 = torch.randn(B, H, Tmax, hd, device="cuda").to(torch.bfloat16)
+    vc0 = torch.randn(B, H, Tmax, hd, device="cuda").to(torch.bfloat16)
+    ang = torch.arange(Tmax).float().view(-1, 1) * (1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))).view(1, -1)
+    cos, sin = ang.cos().to(torch.bfloat16).cuda(), ang.sin().to(torch.bfloat16).cuda()
+    kc, vc = kc0.clone(), vc0.clone()
+    out = torch.empty(B, H * hd, device="cuda", dtype=torch.bfloat16)
+    lens_d = lens.cuda()
+    _lib.check(lib.ovla_decode_rope_attention_ragged(qkv.data_ptr(), 3 * H * hd, cos.data_ptr(), sin.data_ptr(), pos,
+                                                     lens_d.data_ptr(), P, kc.data_ptr(), vc.data_ptr(), B, H, hd, Tmax,
+                                                     out.data_ptr(), H * hd, _lib.stream_ptr()))
+    for b in list(range(min(B, 6))) + ([B - 1] if B > 6 else []):
+        pb = pos - (P - int(lens[b]))
+        k1, v1 = kc0[b:b + 1].clone(), vc0[b:b + 1].clone()
+        o1 = torch.empty(1, H * hd, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.ovla_decode_rope_attention(qkv[b:b + 1].data_ptr(), 3 * H * hd, cos.data_ptr(), sin.data_ptr(), pb,
+                                                  k1.data_ptr(), v1.data_ptr(), 1, H, hd, Tmax, o1.data_ptr(), H * hd,
+                                                  _lib.stream_ptr()))
+        assert torch.equal(out[b], o1[0]), b
+        assert torch.equal(kc[b], k1[0]) and torch.equal(vc[b], v1[0]), b

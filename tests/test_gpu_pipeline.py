@@ -364,3 +364,103 @@ def test_full_size_single_observation_against_fp32_oracle():
     for k, v in errs.items():
         assert v < (6e-2 if "logits" in k else 1.5e-2 if k.startswith("pooled") else 2.5e-2), (k, v)
     model.engine.close()
+
+
+# ----------------------------------------------------------------------------------------------- ragged prompts
+def _ragged(ids, lens, pad):
+    """Right-pad: row b keeps its first lens[b] ids; returns (padded ids, attention mask)."""
+    ids = ids.clone()
+    mask = torch.zeros_like(ids)
+    for b, n in enumerate(lens):
+        ids[b, n:] = pad
+        mask[b, :n] = 1
+    return ids, mask
+
+
+@pytest.mark.parametrize("B,pooling,entry", [(3, "mean", "host"), (4, "final", "device"), (6, "mean", "host"),
+                                             (12, "mean", "device")])
+def test_ragged_batch_rows_equal_their_batch1_results(B, pooling, entry):
+    """Right-padded prompts of different lengths (attention_mask = ones then zeros; reference splice:
+    modeling_prismatic.py:388-390, SURVEY Appendix B "pool over each sample's true length").  Row b of the batch must
+    be what a batch-1 call on its un-padded prompt returns: greedy ids and actions exactly, pooled states to 1e-6 (as
+    test_batch_invariance), and inside the oracle's error envelope.  B = 3 / 4 decode in the persistent kernel, B = 6
+    with the weight-streaming GEMVs + the per-layer decode attention, B = 12 with tcgen05 GEMMs."""
+    P = 12
+    od, pc, W, model, ids, px = _build(B=B, P=P)
+    lens = [P, 5, 9, 1, 7, 12, 3, 2, 11, 6, 4, 8][:B]
+    rid, mask = _ragged(ids, lens, pc.pad_token_id)
+    layers = list(range(od.llm_layers + 1))
+    dev = (lambda t: t.cuda()) if entry == "device" else (lambda t: t)
+    for rep in range(3):                                     # eager, graph capture, graph replay
+        (a_all, t_all), pooled_all = model._predict(dev(rid), "synthetic", capture=True, pooling_method=pooling,
+                                                    pixel_values=dev(px), attention_mask=mask, return_tokens=True)
+        if rep == 0:
+            first = (a_all.copy(), t_all.copy(), pooled_all.copy())
+        else:
+            assert np.array_equal(first[0], a_all) and np.array_equal(first[1], t_all) and np.array_equal(first[2], pooled_all)
+    stats = O.default_stats()
+    for b in range(B):
+        one = ids[b:b + 1, :lens[b]]
+        (a_b, t_b), pooled_b = model._predict(dev(one), "synthetic", capture=True, pooling_method=pooling,
+                                              pixel_values=dev(px[b:b + 1]), return_tokens=True)
+        assert np.array_equal(t_all[b], t_b[0]), (b, lens[b])
+        assert np.array_equal(a_all[b], a_b), (b, lens[b])
+        assert np.allclose(pooled_all[:, b], pooled_b[:, 0], rtol=0, atol=1e-6), (b, lens[b])
+    for b in (1, 3 % B):                                     # oracle envelope on two short rows
+        one = ids[b:b + 1, :lens[b]]
+        with torch.no_grad():
+            e32, _ = O.get_vla_action(to_f32(W), od, one, px[b:b + 1], stats, layers, pooling, dtype=torch.float32)
+            e16, _ = O.get_vla_action(W, od, one, px[b:b + 1], stats, layers, pooling, dtype=torch.bfloat16)
+        for L in layers:
+            ok, info = envelope_ok(pooled_all[L, b:b + 1], e32[L], e16[L])
+            assert ok, f"row {b} (len {lens[b]}) layer {L}: {info}"
+
+
+def test_ragged_lengths_are_read_at_replay_time():
+    """The lengths live in a device buffer the captured pass reads when it runs: the same CUDA graph replayed with other
+    lengths (same shapes, host entry point => same staging pointers) gives the other lengths' results."""
+    B, P = 3, 10
+    od, pc, W, model, ids, px = _build(B=B, P=P)
+    before = model.engine.lib.ovla_graph_replays(model.engine._h)
+    results = {}
+    patterns = [(10, 4, 7), (3, 10, 5), (10, 4, 7), (6, 6, 10)]
+    for lens in patterns:
+        rid, mask = _ragged(ids, lens, pc.pad_token_id)
+        (a, t), pooled = model._predict(rid, "synthetic", capture=True, pixel_values=px, attention_mask=mask,
+                                        return_tokens=True)
+        if lens in results:
+            assert np.array_equal(results[lens][0], t) and np.array_equal(results[lens][1], pooled)
+        results[lens] = (t.copy(), pooled.copy())
+    assert model.engine.lib.ovla_graph_replays(model.engine._h) - before >= 2
+    for lens in patterns[1:2] + patterns[3:]:
+        for b in range(B):
+            (a_b, t_b), pooled_b = model._predict(ids[b:b + 1, :lens[b]], "synthetic", capture=True,
+                                                  pixel_values=px[b:b + 1], return_tokens=True)
+            assert np.array_equal(results[lens][0][b], t_b[0])
+            assert np.allclose(results[lens][1][:, b], pooled_b[:, 0], rtol=0, atol=1e-6)
+
+
+def test_ragged_full_width_against_fp32_oracle():
+    """Real layer widths, T = 288 for the longest row: each ragged row against the fp32 oracle run on its un-padded
+    prompt (rel-L2 <= 1.5e-2 on the pooled states, <= 3e-2 on its first-token logits, as the uniform full-width test),
+    and the decode positions / KV appends of the short rows through the equality of their greedy ids with a batch-1
+    run of the engine."""
+    P = 31
+    od, pc, W, model, ids, px = _build(kind="full-width", B=3, P=P, llm_layers=2)
+    lens = [P, 12, 23]
+    rid, _ = _ragged(ids, lens, pc.pad_token_id)
+    ids29 = torch.cat([rid, torch.full((3, 1), pc.pad_token_id)], 1)
+    for b, n in enumerate(lens):
+        ids29[b, n] = 29871
+    lens29 = torch.tensor([n + 1 for n in lens], dtype=torch.int32)
+    r = model.engine.run(ids29, px, od.n_patches + P, 0, 7, want_logits=True, prompt_lens=lens29)
+    pooled, logits0, tokens = r["pooled"].cpu(), r["step_logits"][0].cpu(), r["tokens"].cpu()
+    for b, n in enumerate(lens):
+        one29 = ids29[b:b + 1, :n + 1]
+        with torch.no_grad():
+            out = O.multimodal_forward(to_f32(W), od, one29, px[b:b + 1], dtype=torch.float32)
+        for i, h in enumerate(out.hidden_states):
+            assert rel_l2(pooled[i, b:b + 1], h[:, : od.n_patches + n].mean(1)) < 1.5e-2, (b, i)
+        assert rel_l2(logits0[b:b + 1], out.logits[:, -1]) < 3e-2, b
+        r1 = model.engine.run(one29, px[b:b + 1], od.n_patches + n, 0, 7)
+        assert torch.equal(r1["tokens"].cpu()[0], tokens[b]), b
