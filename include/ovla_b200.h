@@ -48,6 +48,19 @@ typedef struct OvlaGemmEpilogue {
   const float* bias_f32;  /* [N] or NULL (fp32-output modes only)                                      */
   int gelu;               /* 1: exact-erf GELU after the bias (nn.GELU, modeling_prismatic.py:139-144) */
   int round_bf16;         /* fp32 output: round the value to bf16 first (HF logits.float())            */
+  /* LlamaRMSNorm (transformers modeling_llama.py, reached from modeling_prismatic.py:404-415) fused ACROSS two GEMMs:
+   * the GEMM that writes the residual stream (o_proj / down_proj, OVLA_GEMM_BF16 with resid) also writes per-row
+   * partial sums of squares of the bf16 values it stores: row_sumsq_out[row * row_sumsq_ld + 2 g + p] for the
+   * 128-column group g and 32-column-chunk parity p (N / 64 floats per row, N % 128 == 0);  the GEMM that consumes the
+   * normalised rows (OVLA_GEMM_SWIGLU here, ovla_qkv_rope_gemm_rownorm) is given A = the UN-normalised rows, W = the
+   * weight with the norm weight folded in (ovla_fold_norm_weight) and row_sumsq_in: it scales row r of its fp32
+   * accumulators by rsqrt(sum_{s < row_sumsq_parts} in[r * ld + s] / K + norm_eps) before their first bf16 rounding.
+   * Rounding-point change vs the un-fused path (ovla_rmsnorm, then a plain GEMM): bf16(x * rstd) and the product with
+   * the norm weight are no longer rounded per element; instead the folded weight is rounded once at bind time.  */
+  float* row_sumsq_out;
+  const float* row_sumsq_in;
+  int row_sumsq_ld, row_sumsq_parts;
+  float norm_eps;
 } OvlaGemmEpilogue;
 
 enum { OVLA_GEMM_BF16 = 0, OVLA_GEMM_SWIGLU = 1, OVLA_GEMM_F32OUT = 2 };
@@ -113,6 +126,20 @@ int ovla_detokenize(const long long* ids_dev, int n, int action_dim, int vocab_s
 int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K, int T,
                        int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev, long long ldo,
                        void* k_cache_dev, void* v_cache_dev, int Tmax, int tile_n, int cta_group, void* stream);
+/* ovla_qkv_rope_gemm with the preceding input_layernorm fused (see OvlaGemmEpilogue.row_sumsq_in): a_dev holds the
+ * un-normalised residual rows, w_dev the q|k|v weight with the norm weight folded in. */
+int ovla_qkv_rope_gemm_rownorm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K,
+                               int T, int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev,
+                               long long ldo, void* k_cache_dev, void* v_cache_dev, int Tmax, const float* row_sumsq_in_dev,
+                               int row_sumsq_ld, int row_sumsq_parts, float norm_eps, int tile_n, int cta_group,
+                               void* stream);
+/* partial sums of squares of bf16 rows [rows, D] (D % 128 == 0) in the slot layout of OvlaGemmEpilogue.row_sumsq_out
+ * (the first layer's input comes from the embedding splice, not from a GEMM) */
+int ovla_row_sumsq(const void* x_dev, long long ldx, int rows, int D, float* row_sumsq_out_dev, int row_sumsq_ld,
+                   void* stream);
+/* out[n, k] = bf16(w[n, k] * gamma[k]) for a bf16 [N, K] weight (K % 8 == 0): the RMSNorm weight folded into the
+ * projection that follows it */
+int ovla_fold_norm_weight(const void* w_dev, const void* gamma_dev, void* out_dev, long long N, int K, void* stream);
 /* PrismaticImageProcessor.apply_transform (processing_prismatic.py:128-145) for frames already at model resolution +
  * the bf16 cast of get_vla_action (openvla_utils.py:186): uint8 HWC [B,S,S,3] -> bf16 [B, 3*n_towers, S, S];
  * mean/std: fp32 [n_towers*3] on the device.  Bit-identical to torchvision's to_tensor + normalize on the host. */

@@ -27,6 +27,11 @@ class GemmEpilogue(C.Structure):
         ("bias_f32", C.c_void_p),
         ("gelu", C.c_int),
         ("round_bf16", C.c_int),
+        ("row_sumsq_out", C.c_void_p),
+        ("row_sumsq_in", C.c_void_p),
+        ("row_sumsq_ld", C.c_int),
+        ("row_sumsq_parts", C.c_int),
+        ("norm_eps", C.c_float),
     ]
 
 

@@ -62,6 +62,12 @@ int ovla_gemm(const void* a_dev, long long lda, const void* w_dev, long long ldw
     e.bias_f32 = epi->bias_f32;
     e.gelu = epi->gelu;
     e.round_bf16 = epi->round_bf16;
+    e.ss_out = epi->row_sumsq_out;
+    e.ss_in = epi->row_sumsq_in;
+    e.ss_ld = epi->row_sumsq_ld;
+    e.ss_parts = epi->row_sumsq_parts;
+    e.ss_inv_k = 1.0f / static_cast<float>(K);
+    e.ss_eps = epi->norm_eps;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // do not create a workspace for shapes that never split (gemm.cu)
@@ -97,6 +103,39 @@ int ovla_qkv_rope_gemm(const void* a_dev, long long lda, const void* w_dev, long
   e.H = H;
   return gemm_launch(a_dev, lda, w_dev, ldw, M, 3 * H * 128, K, kModeQkvRope, kKindBf16, e, tile_n, cta_group, num_sms(),
                      static_cast<cudaStream_t>(stream));
+}
+
+int ovla_qkv_rope_gemm_rownorm(const void* a_dev, long long lda, const void* w_dev, long long ldw, int M, int H, int K,
+                               int T, int pos0, const void* cos_dev, const void* sin_dev, void* qkv_out_dev,
+                               long long ldo, void* k_cache_dev, void* v_cache_dev, int Tmax, const float* ss_in, int ss_ld,
+                               int ss_parts, float norm_eps, int tile_n, int cta_group, void* stream) {
+  if (!ss_in) return set_error("ovla_qkv_rope_gemm_rownorm: null row sums");
+  GemmEpi e = {};
+  e.out = qkv_out_dev;
+  e.ldo = ldo;
+  e.rope_cos = static_cast<const __nv_bfloat16*>(cos_dev);
+  e.rope_sin = static_cast<const __nv_bfloat16*>(sin_dev);
+  e.k_cache = static_cast<__nv_bfloat16*>(k_cache_dev);
+  e.v_cache = static_cast<__nv_bfloat16*>(v_cache_dev);
+  e.T = T;
+  e.pos0 = pos0;
+  e.Tmax = Tmax;
+  e.H = H;
+  e.ss_in = ss_in;
+  e.ss_ld = ss_ld;
+  e.ss_parts = ss_parts;
+  e.ss_inv_k = 1.0f / static_cast<float>(K);
+  e.ss_eps = norm_eps;
+  return gemm_launch(a_dev, lda, w_dev, ldw, M, 3 * H * 128, K, kModeQkvRope, kKindBf16, e, tile_n, cta_group, num_sms(),
+                     static_cast<cudaStream_t>(stream));
+}
+int ovla_row_sumsq(const void* x, long long ldx, int rows, int D, float* ss, int ss_ld, void* stream) {
+  if (!x || !ss) return set_error("ovla_row_sumsq: null buffer");
+  return row_sumsq_launch(x, ldx, rows, D, ss, ss_ld, static_cast<cudaStream_t>(stream));
+}
+int ovla_fold_norm_weight(const void* w, const void* gamma, void* out, long long N, int K, void* stream) {
+  if (!w || !gamma || !out) return set_error("ovla_fold_norm_weight: null buffer");
+  return fold_norm_weight_launch(w, gamma, out, N, K, static_cast<cudaStream_t>(stream));
 }
 
 int ovla_gemv(const void* x_dev, long long ldx, const void* w_dev, long long ldw, int M, int N, int K, int mode,

@@ -48,6 +48,9 @@ struct TowerW {
 };
 struct LayerW {
   Slot ln1, qkv_w, o_w, ln2, gate_up_w, down_w;
+  // copies of qkv_w / gate_up_w with the RMSNorm weight of the norm in front folded in (made by ovla_finalize): the
+  // large-batch prefill reads these and applies 1/rms as a row scale in the GEMM epilogue (no stand-alone norm kernel)
+  bf16 *qkv_wn = nullptr, *gate_up_wn = nullptr;
   bool q_bound = false, k_bound = false, v_bound = false, gate_bound = false, up_bound = false;
 };
 
@@ -103,6 +106,14 @@ struct OvlaEngine {
   bool two_streams = true;  // OVLA_TWO_STREAMS=0: towers back to back on one stream
   bool attn_tc = true;    // OVLA_ATTN_TC=0 falls back to the mma.sync flash kernel for head_dim 64 / 128 (A/B runs)
   bool fuse_rope = true;  // OVLA_FUSE_ROPE=0 keeps the stand-alone RoPE kernel (A/B measurements)
+  // OVLA_FUSE_NORM=0 keeps the stand-alone RMSNorm kernels in the large-batch prefill.  Fused: o_proj / down_proj write
+  // per-row partial sums of squares of the residual stream from their epilogues, the following QKV / gate-up GEMM
+  // (norm weight folded into its weights) scales its accumulators by 1/rms.
+  bool fuse_norm = true;
+  int fuse_norm_min_rows = 513;   // below: split-K / weight-streaming shapes keep the un-fused kernels
+                                  // (OVLA_FUSE_NORM_MIN_ROWS at engine creation; tests lower it to reach the path)
+  float* l_ss = nullptr;                         // [max_batch * max_seq, llm_dim / 64] partial sums of squares
+  int ss_ld = 0;
   // ovla_run_host, eager (non-graph) passes: each layer's pooled row block goes to the host on a copy stream as soon
   // as its pooling kernel is done, under the rest of the pass
   float* pooled_host_async = nullptr;
@@ -169,6 +180,8 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   if (const char* tc = getenv("OVLA_ATTN_TC")) e->attn_tc = tc[0] != '0';
   if (const char* fr = getenv("OVLA_FUSE_ROPE")) e->fuse_rope = fr[0] != '0';
   if (const char* ts = getenv("OVLA_TWO_STREAMS")) e->two_streams = ts[0] != '0';
+  if (const char* fn = getenv("OVLA_FUSE_NORM")) e->fuse_norm = fn[0] != '0';
+  if (const char* fr = getenv("OVLA_FUSE_NORM_MIN_ROWS")) e->fuse_norm_min_rows = std::max(1, atoi(fr));
   if (const char* dm = getenv("OVLA_DECODE_MEGA")) e->decode_mega = dm[0] != '0';
   if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
   e->device = device;
@@ -217,6 +230,9 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   }
   A(e->embed, d.vocab, Dl);
   e->layers.resize(d.llm_layers);
+  // the fused-norm prefill needs whole 128-column slots per row and only pays above the split-K regime
+  const bool want_fused_norm = e->fuse_norm && (Dl % 128 == 0) && (1LL * d.max_batch * d.max_seq >= e->fuse_norm_min_rows);
+  e->fuse_norm = want_fused_norm;
   for (LayerW& l : e->layers) {
     A(l.ln1, 1, Dl);
     A(l.qkv_w, 3LL * Dl, Dl);
@@ -224,6 +240,8 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
     A(l.ln2, 1, Dl);
     A(l.gate_up_w, 2LL * d.llm_inter, Dl);
     A(l.down_w, Dl, d.llm_inter);
+    if (want_fused_norm && !rc) rc = e->alloc(&l.qkv_wn, 3LL * Dl * Dl, true);
+    if (want_fused_norm && !rc) rc = e->alloc(&l.gate_up_wn, 2LL * d.llm_inter * Dl, true);
   }
   A(e->final_norm, 1, Dl);
   A(e->lm_head, d.vocab, Dl);
@@ -260,6 +278,10 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   W(&e->l_qkv, B * T * 3 * Dl);
   W(&e->l_attn, B * T * Dl);
   W(&e->l_act, B * T * d.llm_inter);
+  if (e->fuse_norm) {
+    e->ss_ld = Dl / 64;
+    W(&e->l_ss, B * T * e->ss_ld);
+  }
   W(&e->kv, e->kv_layer_elems() * d.llm_layers);
   W(&e->pooled, (d.llm_layers + 1LL) * B * Dl);
   W(&e->logits, B * d.vocab);
@@ -454,6 +476,10 @@ extern "C" int ovla_set_option(OvlaEngine* e, const char* name, int value) {
   else if (n == "attn_tc") e->attn_tc = value != 0;
   else if (n == "fuse_rope") e->fuse_rope = value != 0;
   else if (n == "two_streams") e->two_streams = value != 0;
+  else if (n == "fuse_norm") {
+    if (value && !e->l_ss) return set_error("ovla_set_option: engine was created without the fused-norm weights (OVLA_FUSE_NORM=0 or a small engine)");
+    e->fuse_norm = value != 0;
+  }
   else if (n == "graph_max_batch") e->graph_max_batch = value;
   else return set_error("ovla_set_option: unknown option '%s'", name);
   // captured passes embed the old choice
@@ -503,6 +529,13 @@ extern "C" int ovla_finalize(OvlaEngine* e) {
   }
   if (n_missing) return set_error("ovla_finalize: %d tensors not bound (%s%s)", n_missing, missing.c_str(),
                                   n_missing > 6 ? ", ..." : "");
+  if (e->fuse_norm) {  // fold the norm weights into the copies the fused-norm prefill multiplies with
+    for (LayerW& l : e->layers) {
+      OVLA_TRY(fold_norm_weight_launch(l.qkv_w.ptr, l.ln1.ptr, l.qkv_wn, l.qkv_w.rows, static_cast<int>(l.qkv_w.cols), nullptr));
+      OVLA_TRY(fold_norm_weight_launch(l.gate_up_w.ptr, l.ln2.ptr, l.gate_up_wn, l.gate_up_w.rows,
+                                       static_cast<int>(l.gate_up_w.cols), nullptr));
+    }
+  }
   {  // weight-pointer table of the persistent decode-step kernel
     std::vector<DecodeLayerPtrs> tab(e->layers.size());
     for (size_t i = 0; i < e->layers.size(); ++i) {
@@ -594,6 +627,13 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
   const long long s12[12] = {3LL * D * T, 3LL * D, hd,                                   // q in the fused buffer
                              1LL * H * Tmax * hd, hd, 1LL * Tmax * hd,                   // k cache [B,H,Tmax,hd]
                              1LL * H * Tmax * hd, hd, 1LL * Tmax * hd, 1LL * D * T, D, hd};
+  // RMSNorm fused into the GEMMs on both sides of it (large batches): see OvlaEngine::fuse_norm
+  const bool fnorm = e->fuse_norm && e->fuse_rope && e->l_ss && rows >= e->fuse_norm_min_rows && d.llm_layers > 0;
+  auto norm_in = [&](GemmEpi& epi) {
+    epi.ss_in = e->l_ss; epi.ss_ld = e->ss_ld; epi.ss_parts = D / 64; epi.ss_inv_k = 1.0f / static_cast<float>(D);
+    epi.ss_eps = d.rms_eps;
+  };
+  if (fnorm) OVLA_TRY(row_sumsq_launch(e->l_x, D, rows, D, e->l_ss, e->ss_ld, st));   // layer 0's input comes from no GEMM
   for (int i = 0; i < d.llm_layers; ++i) {
     LayerW& l = e->layers[i];
     if (a->pool_len > 0)
@@ -603,7 +643,7 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
     if (a->hidden_out_dev)
       CUDA_TRY(cudaMemcpyAsync(static_cast<bf16*>(a->hidden_out_dev) + 1LL * i * rows * D, e->l_x,
                                sizeof(bf16) * rows * D, cudaMemcpyDeviceToDevice, st));
-    OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, rows, D, st));
+    if (!fnorm) OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln1.ptr, d.rms_eps, e->l_h, D, rows, D, st));
     if (e->fuse_rope) {  // QKV projection with RoPE + KV-cache write fused into the GEMM epilogue
       GemmEpi epi = {};
       epi.out = e->l_qkv;
@@ -616,7 +656,9 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       epi.pos0 = 0;
       epi.Tmax = Tmax;
       epi.H = H;
-      OVLA_TRY(gemm_launch(e->l_h, D, l.qkv_w.ptr, D, rows, 3 * D, D, kModeQkvRope, kKindBf16, epi, 0, 0, num_sms(), st));
+      if (fnorm) norm_in(epi);
+      OVLA_TRY(gemm_launch(fnorm ? e->l_x : e->l_h, D, fnorm ? l.qkv_wn : l.qkv_w.ptr, D, rows, 3 * D, D, kModeQkvRope,
+                           kKindBf16, epi, 0, 0, num_sms(), st));
     } else {
       OVLA_TRY(linear(e, e->l_h, D, l.qkv_w, rows, kModeBf16, e->l_qkv, 3LL * D, nullptr, nullptr, nullptr, 0, 0, 0, st));
       OVLA_TRY(rope_kv_launch(e->l_qkv, B, T, H, hd, 0, e->rope_cos.ptr, e->rope_sin.ptr, e->k_cache(i), e->v_cache(i),
@@ -626,6 +668,22 @@ int run_prefill(OvlaEngine* e, int B, int T, const OvlaRunArgs* a, cudaStream_t 
       OVLA_TRY(attn_tc_prefill_launch(e->l_qkv, 3LL * D, e->k_cache(i), e->v_cache(i), e->l_attn, D, B, H, T, Tmax, st));
     else
       OVLA_TRY(flash_attn_launch(e->l_qkv, e->k_cache(i), e->v_cache(i), e->l_attn, s12, B, H, T, T, hd, 1, st));
+    if (fnorm) {
+      // x += o_proj(attn), the epilogue also leaving the row sums of squares of the new x; gate/up reads x itself
+      GemmEpi eo = {};
+      eo.out = e->l_x; eo.ldo = D; eo.resid = e->l_x; eo.ldr = D;
+      eo.ss_out = e->l_ss; eo.ss_ld = e->ss_ld;
+      OVLA_TRY(gemm_launch(e->l_attn, D, l.o_w.ptr, D, rows, D, D, kModeBf16, kKindBf16, eo, 0, 0, num_sms(), st));
+      GemmEpi eg = {};
+      eg.out = e->l_act; eg.ldo = d.llm_inter;
+      norm_in(eg);
+      OVLA_TRY(gemm_launch(e->l_x, D, l.gate_up_wn, D, rows, 2 * d.llm_inter, D, kModeSwiGLU, kKindBf16, eg, 0, 0, num_sms(), st));
+      GemmEpi ed = eo;   // x += down(act), again with the row sums for the next layer's input norm
+      if (i + 1 == d.llm_layers) ed.ss_out = nullptr;   // the final norm is a stand-alone kernel (its output is pooled)
+      OVLA_TRY(gemm_launch(e->l_act, d.llm_inter, l.down_w.ptr, d.llm_inter, rows, D, d.llm_inter, kModeBf16, kKindBf16, ed, 0,
+                           0, num_sms(), st));
+      continue;
+    }
     OVLA_TRY(linear(e, e->l_attn, D, l.o_w, rows, kModeBf16, e->l_x, D, nullptr, nullptr, e->l_x, D, 0, 0, st));
     OVLA_TRY(rmsnorm_launch(e->l_x, D, l.ln2.ptr, d.rms_eps, e->l_h, D, rows, D, st));
     OVLA_TRY(linear(e, e->l_h, D, l.gate_up_w, rows, kModeSwiGLU, e->l_act, d.llm_inter, nullptr, nullptr, nullptr, 0, 0,

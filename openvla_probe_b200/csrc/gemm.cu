@@ -192,6 +192,16 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
       return set_error("gemm: fused QKV+RoPE needs cos/sin tables, KV caches and M = B * T");
     if (epi.pos0 + epi.T > epi.Tmax) return set_error("gemm: position %d exceeds KV capacity %d", epi.pos0 + epi.T, epi.Tmax);
   }
+  const bool fused_norm = epi.ss_out || epi.ss_in;
+  if (epi.ss_out) {
+    if (mode != kModeBf16 || kind != kKindBf16 || (N % 128)) return set_error("gemm: sum-of-squares output needs a bf16 GEMM with N %% 128 == 0");
+    if (epi.ss_ld < N / 64 || (epi.ss_ld % 4)) return set_error("gemm: sum-of-squares pitch %d below %d slots (or not a multiple of 4)", epi.ss_ld, N / 64);
+  }
+  if (epi.ss_in) {
+    if (mode != kModeQkvRope && mode != kModeSwiGLU) return set_error("gemm: a row-norm input needs the QKV+RoPE or SwiGLU epilogue");
+    if (epi.ss_parts <= 0 || (epi.ss_parts % 4) || epi.ss_parts > epi.ss_ld || (epi.ss_ld % 4) || (reinterpret_cast<uintptr_t>(epi.ss_in) & 15))
+      return set_error("gemm: row-norm input needs 16-byte aligned rows of a multiple of 4 partial sums");
+  }
   const bool auto_tile = bn <= 0;
   if (bn <= 0) {
     // Tile heuristic.  Large problems: CTA-pair 256x256 tiles (tensor-bound).  Small M (bs=1 prefill, M = 261..288,
@@ -210,6 +220,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   }
   if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");
   if (mode == kModeQkvRope && bn < 128) { bn = 128; cg = 1; }  // a tile must hold whole 128-wide heads
+  if (epi.ss_out && bn < 128) { bn = 128; cg = 1; }            // a thread must own whole (128-column group, parity) slots
   // rasterisation group (tools/gemm_group_sweep.py, profiles/r01_gemm_group_sweep.jsonl): 16 row-tiles keep the
   // activation slab of a group L2-resident while the weights stream; narrow, short-K problems prefer 8
   static int g_group = -1, g_split = -2;
@@ -231,7 +242,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   // split-K for the small-M weight-streaming shapes (see splitk.cu)
   const int num_k = (K + (128 / eb) - 1) / (128 / eb);
   int split = 1;
-  if (auto_tile && g_split != 0 && g_split != 1 && splitk_eligible(M, N, kind) &&
+  if (auto_tile && !fused_norm && g_split != 0 && g_split != 1 && splitk_eligible(M, N, kind) &&
       (kind == kKindBf16 ? (mode == kModeBf16 || mode == kModeSwiGLU || mode == kModeF32) : mode == kModeF32) && (mode == kModeSwiGLU ? (N / 2) % 8 == 0 : N % 8 == 0)) {
     if (kind == kKindBf16 && N < 8192) { bn = 128; cg = 1; }
     const long long tiles_mn = ((M + 128LL * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);

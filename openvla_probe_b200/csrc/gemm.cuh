@@ -48,7 +48,42 @@ struct GemmEpi {
   int tma_epi;  // kModeBf16: output (and residual) tiles move through shared memory with TMA (tensor maps passed beside)
   // grouped GEMM (GemmShape::groups > 1, kModeF32 only): element strides between the groups' outputs / fp32 biases
   long long out_gs, bias_gs;
+  // RMSNorm fused across two GEMMs (LlamaRMSNorm between o_proj / down_proj and the next q,k,v / gate,up projection):
+  //   producer (kModeBf16): ss_out[row * ss_ld + slot] = sum of squares of the bf16 values this GEMM stores in the
+  //     128-column group g = col / 128, over the 32-column chunks of parity p = (col / 32) & 1; slot = 2 g + p
+  //     (a fixed partition, independent of the tile shape, written once by one thread: deterministic);
+  //   consumer (kModeQkvRope / kModeSwiGLU): every accumulator of `row` is multiplied by
+  //     rsqrt(sum_{s < ss_parts} ss_in[row * ss_ld + s] * ss_inv_k + ss_eps) before its first bf16 rounding; the
+  //     norm weight is folded into W beforehand (fold_norm_weight_launch).
+  float* ss_out;
+  const float* ss_in;
+  int ss_ld, ss_parts;
+  float ss_inv_k, ss_eps;
 };
+
+// consumer side of the fused RMSNorm: the row's 1/rms from the producer's partial sums (fixed summation order).  Called
+// BEFORE the wait for the accumulator, so that the loads (issued together, 16 at a time) ride under the tile's main loop.
+__device__ __forceinline__ float fused_norm_rstd(const GemmEpi& epi, int row, bool row_ok) {
+  if (!epi.ss_in) return 1.f;
+  float ss = 0.f;
+  if (row_ok) {
+    const float4* p = reinterpret_cast<const float4*>(epi.ss_in + static_cast<long long>(row) * epi.ss_ld);
+    const int n4 = epi.ss_parts / 4;
+    for (int j0 = 0; j0 < n4; j0 += 16) {
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (j0 + j < n4) ? p[j0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        ss += v[j].x;
+        ss += v[j].y;
+        ss += v[j].z;
+        ss += v[j].w;
+      }
+    }
+  }
+  return rsqrtf(ss * epi.ss_inv_k + epi.ss_eps);
+}
 
 struct GemmShape {
   int M, N, K;  // N = rows of W (pre-epilogue output columns); K in elements
@@ -247,10 +282,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int outer = t / tiles_mn;
       const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
       gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
       const bool row_ok = row < shape.M;
+      float rstd = 1.f;
+      if constexpr (MODE == kModeSwiGLU || MODE == kModeQkvRope) rstd = fused_norm_rstd(epi, row, row_ok);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const int col0 = nb * BN;
 
@@ -281,6 +318,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         };
 #pragma unroll
         for (int i = 0; i < SL; ++i) fetch_res(part + 2 * i);
+        float ss0 = 0.f, ss1 = 0.f;   // fused RMSNorm producer: this row's sums of squares, first / second 128 columns
 #pragma unroll 1
         for (int c = part; c < BN / 32; c += 2) {
           const int col = col0 + c * 32;
@@ -288,6 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
+          float cs = 0.f;
           uint4 rr[4] = {};
           if (has_res) {
             const uint32_t sl = n_res % SL;
@@ -355,7 +394,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             o4[g].y = pack_bf16(x[2], x[3]);
             o4[g].z = pack_bf16(x[4], x[5]);
             o4[g].w = pack_bf16(x[6], x[7]);
+            if (epi.ss_out) {   // squares of the values as stored (bf16), in column order
+              const uint32_t ow[4] = {o4[g].x, o4[g].y, o4[g].z, o4[g].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 r = unpack_bf16(ow[i]);
+                cs = fmaf(r.x, r.x, cs);
+                cs = fmaf(r.y, r.y, cs);
+              }
+            }
           }
+          if (c & 4) ss1 += cs; else ss0 += cs;
           uint8_t* so = out_slot(n_out);
           if (lane == 0) tma_store_wait_read<SL - 1>();   // the store that last used this slot has finished reading it
           __syncwarp();
@@ -368,6 +417,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_commit();
           }
           ++n_out;
+        }
+        if (epi.ss_out && row_ok && col0 < shape.N) {
+          float* sp = epi.ss_out + static_cast<long long>(row) * epi.ss_ld + (col0 >> 7) * 2 + part;
+          sp[0] = ss0;
+          if (BN > 128 && col0 + 128 < shape.N) sp[2] = ss1;
         }
       } else if constexpr (MODE == kModeBf16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.out) + static_cast<long long>(row) * epi.ldo;
@@ -383,6 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (res && c < BN / 32 && col + g * 8 < shape.N) dst[g] = *reinterpret_cast<const uint4*>(res + col + g * 8);
         };
         fetch_resid(part, rr);
+        float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
         for (int c = part; c < BN / 32; c += 2) {
           uint32_t v[32];
@@ -391,6 +446,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fetch_resid(c + 2, rn);
           tmem_ld_wait();
           const int col = col0 + c * 32;
+          float cs = 0.f;
           if (col < shape.N) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte store
@@ -445,11 +501,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 o.z = pack_bf16(x[4], x[5]);
                 o.w = pack_bf16(x[6], x[7]);
                 *reinterpret_cast<uint4*>(out + cg) = o;
+                if (epi.ss_out) {
+                  const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 r = unpack_bf16(ow[i]);
+                    cs = fmaf(r.x, r.x, cs);
+                    cs = fmaf(r.y, r.y, cs);
+                  }
+                }
               }
             }
           }
+          if (c & 4) ss1 += cs; else ss0 += cs;
 #pragma unroll
           for (int g = 0; g < 4; ++g) rr[g] = rn[g];
+        }
+        if (epi.ss_out && row_ok && col0 < shape.N) {
+          float* sp = epi.ss_out + static_cast<long long>(row) * epi.ss_ld + (col0 >> 7) * 2 + part;
+          sp[0] = ss0;
+          if (BN > 128 && col0 + 128 < shape.N) sp[2] = ss1;
         }
       } else if (MODE == kModeSwiGLU && epi.tma_epi) {
         // same shared-memory + TMA store as the bf16 mode: a 64-column accumulator chunk ([32 gate | 32 up]) gives one
@@ -473,8 +544,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]));
-              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]));
+              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]) * rstd);
+              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]) * rstd);
               y[i] = bf16_round(silu(gv)) * uv;
             }
             o4[grp].x = pack_bf16(y[0], y[1]);
@@ -513,8 +584,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]));
-              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]));
+              const float gv = bf16_round(__uint_as_float(g[grp * 8 + i]) * rstd);
+              const float uv = bf16_round(__uint_as_float(u[grp * 8 + i]) * rstd);
               y[i] = bf16_round(silu(gv)) * uv;
             }
             if (row_ok) {
@@ -562,8 +633,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 c = unpack_bf16(cw[i]), sI = unpack_bf16(sw[i]);
-                  const float a0 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i])), a1 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i + 1]));
-                  const float b0 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i])), b1 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i + 1]));
+                  const float a0 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i]) * rstd), a1 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i + 1]) * rstd);
+                  const float b0 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i]) * rstd), b1 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i + 1]) * rstd);
                   o1[2 * i] = bf16_round(a0 * c.x) + bf16_round(-b0 * sI.x);
                   o1[2 * i + 1] = bf16_round(a1 * c.y) + bf16_round(-b1 * sI.y);
                   o2[2 * i] = bf16_round(b0 * c.x) + bf16_round(a0 * sI.x);
@@ -572,8 +643,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  o1[i] = __uint_as_float(lo[g * 8 + i]);
-                  o2[i] = __uint_as_float(hi[g * 8 + i]);
+                  o1[i] = __uint_as_float(lo[g * 8 + i]) * rstd;
+                  o2[i] = __uint_as_float(hi[g * 8 + i]) * rstd;
                 }
               }
               uint4 w1, w2;

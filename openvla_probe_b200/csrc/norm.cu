@@ -203,6 +203,77 @@ static int norm_dispatch(const void* x, long long ldx, const void* w, const void
   return set_error("norm: unreachable");
 }
 
+// ---- RMSNorm fused into the neighbouring GEMMs (see GemmEpi::ss_out / ss_in in gemm.cuh) ----------------------------
+// Partial sums of squares of a bf16 row in the slot layout the GEMM epilogue produces: slot 2 g + p = 128-column
+// group g, 32-column chunks of parity p.  Used for the first layer's input (the spliced embeddings come from no GEMM).
+__global__ void __launch_bounds__(128) row_sumsq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int D,
+                                                        float* __restrict__ ss, int ss_ld) {
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* xr = x + static_cast<long long>(row) * ldx;
+  for (int blk = warp; blk * 256 < D; blk += 4) {
+    const int col = blk * 256 + lane * 8;
+    float sq = 0.f;
+    if (col < D) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + col);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(u[i]);
+        sq = fmaf(f.x, f.x, sq);
+        sq = fmaf(f.y, f.y, sq);
+      }
+    }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);   // 4 lanes = one 32-column chunk
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 8);   // chunk c with chunk c + 2 of the same group
+    if ((lane & 11) == 0 && col < D)             // lanes 0, 4, 16, 20: (group, parity) = (lane >> 4, (lane >> 2) & 1)
+      ss[static_cast<long long>(row) * ss_ld + (blk * 2 + (lane >> 4)) * 2 + ((lane >> 2) & 1)] = sq;
+  }
+}
+
+int row_sumsq_launch(const void* x, long long ldx, int rows, int D, float* ss, int ss_ld, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (D % 128) return set_error("row_sumsq: D=%d must be a multiple of 128", D);
+  if (ss_ld < D / 64) return set_error("row_sumsq: pitch %d below the %d partial sums of a row", ss_ld, D / 64);
+  ProfScope prof(kCatNorm, 0.0, 2.0 * rows * D, st);
+  row_sumsq_kernel<<<rows, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, D, ss, ss_ld);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// out[n, k] = bf16(w[n, k] * gamma[k]): the RMSNorm weight folded into the projection that consumes the normalised
+// rows (one extra bf16 rounding of the weights, done once at bind time)
+__global__ void fold_norm_weight_kernel(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ gamma,
+                                        __nv_bfloat16* __restrict__ out, long long total_vec, int kv) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int c = static_cast<int>(idx % kv) * 8;
+  const uint4 wv = reinterpret_cast<const uint4*>(w)[idx];
+  const uint4 gv = *reinterpret_cast<const uint4*>(gamma + c);
+  const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w}, gu[4] = {gv.x, gv.y, gv.z, gv.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = unpack_bf16(wu[i]), g = unpack_bf16(gu[i]);
+    o[i] = pack_bf16(a.x * g.x, a.y * g.y);
+  }
+  reinterpret_cast<uint4*>(out)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int fold_norm_weight_launch(const void* w, const void* gamma, void* out, long long N, int K, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (K % 8) return set_error("fold_norm_weight: K=%d must be a multiple of 8", K);
+  const long long total = N * (K / 8);
+  fold_norm_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(out),
+      total, K / 8);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int layernorm_launch(const void* x, long long ldx, const void* w, const void* b, float eps, void* out, long long ldo,
                      int rows, int D, cudaStream_t st) {
   if (rows <= 0) return 0;

@@ -65,6 +65,11 @@ int layernorm_launch(const void* x, long long ldx, const void* w, const void* b,
 int rmsnorm_launch(const void* x, long long ldx, const void* w, float eps, void* out, long long ldo, int rows, int D,
                    cudaStream_t st);
 
+// fused RMSNorm support (GemmEpi::ss_out / ss_in): per-row partial sums of squares in the GEMM epilogue's slot layout
+// ([rows, ss_ld] floats, D / 64 slots per row), and the norm weight folded into the consuming projection
+int row_sumsq_launch(const void* x, long long ldx, int rows, int D, float* ss, int ss_ld, cudaStream_t st);
+int fold_norm_weight_launch(const void* w, const void* gamma, void* out, long long N, int K, cudaStream_t st);
+
 // attention.cu
 int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
                       int Tq, int Tk, int head_dim, int causal, cudaStream_t st);

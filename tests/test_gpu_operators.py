@@ -598,3 +598,189 @@ def test_decode_attention_ragged_rows_equal_uniform_calls(B):
                                                   _lib.stream_ptr()))
         assert torch.equal(out[b], o1[0]), b
         assert torch.equal(kc[b], k1[0]) and torch.equal(vc[b], v1[0]), b
+
+
+# ----------------------------------------------------------------------------------------------- RMSNorm fused into the GEMMs
+def _slot_sumsq(x32, N):
+    """Reference of the partial-sum layout: slot 2 g + p = 128-column group g, 32-column chunks of parity p."""
+    M = x32.shape[0]
+    sq = (x32.double() ** 2).view(M, N // 128, 2, 2, 32)          # [group, pair, parity, 32]
+    return sq.sum(dim=(2, 4)).reshape(M, N // 64)
+
+
+def _rms_ref(x, gamma, eps):
+    """LlamaRMSNorm on bf16 input in exact arithmetic (no intermediate rounding): the fp32-oracle view."""
+    x64 = x.double()
+    return gamma.double() * (x64 * torch.rsqrt((x64 ** 2).mean(-1, keepdim=True) + eps))
+
+
+def test_row_sumsq_and_fold_norm_weight(L):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(5)
+    for rows, D in [(7, 256), (300, 4096), (33, 384)]:
+        x = bf(torch.randn(rows, D, generator=g) * torch.rand(rows, 1, generator=g) * 30).cuda()
+        ss = torch.full((rows, D // 64 + 4), -1.0, device="cuda")
+        _lib.check(lib.ovla_row_sumsq(P(x), C.c_longlong(D), rows, D, P(ss), D // 64 + 4, None))
+        ref = _slot_sumsq(x.float().cpu(), D)
+        assert torch.allclose(ss[:, : D // 64].double().cpu(), ref, rtol=1e-5, atol=0)
+        assert bool((ss[:, D // 64:] == -1).all())
+    W = bf(torch.randn(704, 256, generator=g) * 0.05).cuda()
+    gam = bf(1 + 0.2 * torch.randn(256, generator=g)).cuda()
+    out = torch.empty_like(W)
+    _lib.check(lib.ovla_fold_norm_weight(P(W), P(gam), P(out), C.c_longlong(704), 256, None))
+    assert torch.equal(out, (W.float() * gam.float()).bfloat16())
+    assert lib.ovla_row_sumsq(P(W), C.c_longlong(200), 4, 200, P(out), 8, None) != 0       # D % 128 != 0
+
+
+@pytest.mark.parametrize("M,N,K,bn,cg", [(1100, 4096, 4096, 0, 0), (1100, 4096, 1024, 128, 1), (300, 256, 192, 0, 0),
+                                         (700, 1024, 512, 256, 1), (2500, 512, 256, 128, 2), (1100, 4096, 4096, -1, 0)])
+def test_gemm_residual_epilogue_writes_row_sums_of_squares(L, M, N, K, bn, cg):
+    """Producer half of the fused RMSNorm: the in-place residual GEMM (o_proj / down_proj) also leaves, per row, the
+    partial sums of squares of the bf16 values it stores -- equal (fp32 round-off) to the sums recomputed from its own
+    output, in the fixed slot layout, for every tile shape; the output itself is bit-identical to the plain call.
+    bn = -1: the direct-store epilogue (OVLA_GEMM_TMA_EPI=0 is read once per process, so it runs in a child)."""
+    _lib, lib = L
+    if bn == -1:
+        import subprocess, sys, os
+        code = ("import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.'); import test_gpu_operators as t;"
+                "from openvla_probe_b200 import _lib;"
+                "t._sumsq_producer_case((_lib, _lib.load()), %d, %d, %d, 0, 0)" % (M, N, K))
+        env = dict(os.environ, OVLA_GEMM_TMA_EPI="0")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        return
+    _sumsq_producer_case(L, M, N, K, bn, cg)
+
+
+def _sumsq_producer_case(L, M, N, K, bn, cg):
+    _lib, lib = L
+    g = torch.Generator().manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, generator=g) * 0.5).cuda()
+    W = bf(torch.randn(N, K, generator=g) * 0.05).cuda()
+    x0 = bf(torch.randn(M, N, generator=g) * (1 + 20 * torch.rand(M, 1, generator=g))).cuda()
+    outs = []
+    for with_ss in (0, 1):
+        x = x0.clone()
+        ss = torch.full((M, N // 64), float("nan"), device="cuda")
+        epi = _lib.GemmEpilogue()
+        epi.resid_bf16, epi.ld_resid = x.data_ptr(), N
+        if with_ss:
+            epi.row_sumsq_out, epi.row_sumsq_ld = ss.data_ptr(), N // 64
+        _lib.check(lib.ovla_gemm(P(A), C.c_longlong(K), P(W), C.c_longlong(K), M, N, K, 0, 0, P(x), C.c_longlong(N),
+                                 C.byref(epi), bn, cg, None))
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1])
+    ref = _slot_sumsq(outs[1].float().cpu(), N)
+    got = ss.double().cpu()
+    assert bool(torch.isfinite(got).all())
+    assert torch.allclose(got, ref, rtol=2e-5, atol=0), float(((got - ref).abs() / ref).max())
+    for _ in range(2):                                     # deterministic: plain stores, no atomics
+        x = x0.clone()
+        ss2 = torch.zeros_like(ss)
+        epi.resid_bf16, epi.row_sumsq_out = x.data_ptr(), ss2.data_ptr()
+        _lib.check(lib.ovla_gemm(P(A), C.c_longlong(K), P(W), C.c_longlong(K), M, N, K, 0, 0, P(x), C.c_longlong(N),
+                                 C.byref(epi), bn, cg, None))
+        assert torch.equal(ss2, ss)
+
+
+@pytest.mark.parametrize("M,K,I,bn,cg", [(600, 256, 704, 0, 0), (1100, 4096, 1408, 0, 0), (300, 512, 256, 128, 1),
+                                         (520, 1024, 512, 256, 2)])
+def test_fused_rmsnorm_swiglu_gemm(L, M, K, I, bn, cg):
+    """Consumer half: gate/up GEMM on the UN-normalised rows with the norm weight folded into W and 1/rms applied to
+    the fp32 accumulators (row sums of squares from ovla_row_sumsq) against exact arithmetic; the fused result may be
+    at most as far from it as 1.5x the un-fused device path (ovla_rmsnorm, then the plain SwiGLU GEMM) + 1 bf16 ulp of
+    the row scale -- it skips two per-element roundings and adds one rounding of the weights."""
+    _lib, lib = L
+    eps = 1e-5
+    g = torch.Generator().manual_seed(M + K)
+    x = bf(torch.randn(M, K, generator=g) * (0.2 + 30 * torch.rand(M, 1, generator=g)))
+    gam = bf(1 + 0.3 * torch.randn(K, generator=g))
+    Wg, Wu = bf(torch.randn(I, K, generator=g) * 0.06), bf(torch.randn(I, K, generator=g) * 0.06)
+    h = _rms_ref(x, gam, eps)
+    ref = (F.silu(h @ Wg.double().t()) * (h @ Wu.double().t())).float()
+    Wi = torch.stack([Wg.view(I // 32, 32, K), Wu.view(I // 32, 32, K)], 1).reshape(2 * I, K).contiguous().cuda()
+    xd, gd = x.cuda(), gam.cuda()
+    # un-fused device path
+    hd_ = torch.empty_like(xd)
+    _lib.check(lib.ovla_rmsnorm(P(xd), C.c_longlong(K), P(gd), C.c_float(eps), P(hd_), C.c_longlong(K), M, K, None))
+    plain = torch.empty(M, I, dtype=torch.bfloat16, device="cuda")
+    epi = _lib.GemmEpilogue()
+    _lib.check(lib.ovla_gemm(P(hd_), C.c_longlong(K), P(Wi), C.c_longlong(K), M, 2 * I, K, 1, 0, P(plain), C.c_longlong(I),
+                             C.byref(epi), bn, cg, None))
+    # fused
+    ss = torch.empty(M, K // 64, device="cuda")
+    _lib.check(lib.ovla_row_sumsq(P(xd), C.c_longlong(K), M, K, P(ss), K // 64, None))
+    Wn = torch.empty_like(Wi)
+    _lib.check(lib.ovla_fold_norm_weight(P(Wi), P(gd), P(Wn), C.c_longlong(2 * I), K, None))
+    fused = torch.empty(M, I, dtype=torch.bfloat16, device="cuda")
+    epi = _lib.GemmEpilogue()
+    epi.row_sumsq_in, epi.row_sumsq_ld, epi.row_sumsq_parts, epi.norm_eps = ss.data_ptr(), K // 64, K // 64, eps
+    _lib.check(lib.ovla_gemm(P(xd), C.c_longlong(K), P(Wn), C.c_longlong(K), M, 2 * I, K, 1, 0, P(fused), C.c_longlong(I),
+                             C.byref(epi), bn, cg, None))
+    scale = ref.abs().amax(-1, keepdim=True).clamp_min(1e-6)
+    e_f = float(((fused.float().cpu() - ref).abs() / scale).max())
+    e_p = float(((plain.float().cpu() - ref).abs() / scale).max())
+    assert e_f <= 1.5 * e_p + 2.0 ** -8, (e_f, e_p)
+    rl_f = float((fused.float().cpu() - ref).norm() / ref.norm())
+    rl_p = float((plain.float().cpu() - ref).norm() / ref.norm())
+    assert rl_f <= 1.25 * rl_p + 1e-4, (rl_f, rl_p)
+    # a norm input is refused by the epilogues that do not implement it
+    bad = _lib.GemmEpilogue()
+    bad.row_sumsq_in, bad.row_sumsq_ld, bad.row_sumsq_parts = ss.data_ptr(), K // 64, K // 64
+    assert lib.ovla_gemm(P(xd), C.c_longlong(K), P(Wn), C.c_longlong(K), M, 2 * I, K, 0, 0, P(Wn), C.c_longlong(2 * I),
+                         C.byref(bad), bn, cg, None) != 0
+
+
+@pytest.mark.parametrize("B,T,H,bn,cg", [(3, 200, 2, 0, 0), (4, 288, 4, 256, 2), (2, 130, 2, 128, 1)])
+def test_fused_rmsnorm_qkv_rope_gemm(L, B, T, H, bn, cg):
+    """input_layernorm fused into the QKV + RoPE + KV-write GEMM against the un-fused device path (ovla_rmsnorm, then
+    ovla_qkv_rope_gemm) and exact arithmetic: rotated q, and the k / v rows written to the cache."""
+    _lib, lib = L
+    from openvla_probe_b200.engine import rope_tables
+
+    hd, Tmax, K, eps = 128, T + 5, 512, 1e-5
+    D, M = H * hd, B * T
+    g = torch.Generator().manual_seed(T + H)
+    x = bf(torch.randn(M, K, generator=g) * (0.2 + 30 * torch.rand(M, 1, generator=g))).cuda()
+    gam = bf(1 + 0.3 * torch.randn(K, generator=g)).cuda()
+    W = bf(torch.randn(3 * D, K, generator=g) * 0.08).cuda()
+    cos, sin = rope_tables(hd, 10000.0, Tmax)
+    cd, sd = cos.cuda(), sin.cuda()
+    h = torch.empty_like(x)
+    _lib.check(lib.ovla_rmsnorm(P(x), C.c_longlong(K), P(gam), C.c_float(eps), P(h), C.c_longlong(K), M, K, None))
+    q0 = torch.zeros(M, 3 * D, dtype=torch.bfloat16, device="cuda")
+    kc0 = torch.zeros(B, H, Tmax, hd, dtype=torch.bfloat16, device="cuda")
+    vc0 = torch.zeros_like(kc0)
+    _lib.check(lib.ovla_qkv_rope_gemm(P(h), C.c_longlong(K), P(W), C.c_longlong(K), M, H, K, T, 0, P(cd), P(sd), P(q0),
+                                      C.c_longlong(3 * D), P(kc0), P(vc0), Tmax, bn, cg, None))
+    ss = torch.empty(M, K // 64, device="cuda")
+    _lib.check(lib.ovla_row_sumsq(P(x), C.c_longlong(K), M, K, P(ss), K // 64, None))
+    Wn = torch.empty_like(W)
+    _lib.check(lib.ovla_fold_norm_weight(P(W), P(gam), P(Wn), C.c_longlong(3 * D), K, None))
+    q1 = torch.zeros_like(q0)
+    kc1, vc1 = torch.zeros_like(kc0), torch.zeros_like(kc0)
+    _lib.check(lib.ovla_qkv_rope_gemm_rownorm(P(x), C.c_longlong(K), P(Wn), C.c_longlong(K), M, H, K, T, 0, P(cd), P(sd),
+                                              P(q1), C.c_longlong(3 * D), P(kc1), P(vc1), Tmax, P(ss), K // 64, K // 64,
+                                              C.c_float(eps), bn, cg, None))
+    # exact reference: v needs no rotation; q, k through the bf16 cos / sin tables in fp64
+    hx = _rms_ref(x.cpu(), gam.cpu(), eps)
+    qkv = hx @ W.double().cpu().t()
+    pos = torch.arange(T).repeat(B)
+    c64, s64 = cos.double()[pos], sin.double()[pos]                      # [M, 64]
+
+    def rot(t):                                                          # [M, H, 128]
+        a, b = t[..., :64], t[..., 64:]
+        return torch.cat([a * c64[:, None] - b * s64[:, None], b * c64[:, None] + a * s64[:, None]], -1)
+
+    q_ref = rot(qkv[:, :D].view(M, H, hd)).reshape(M, D)
+    k_ref = rot(qkv[:, D:2 * D].view(M, H, hd)).view(B, T, H, hd).permute(0, 2, 1, 3)
+    v_ref = qkv[:, 2 * D:].view(B, T, H, hd).permute(0, 2, 1, 3)
+    for name, f, p, r in [("q", q1[:, :D], q0[:, :D], q_ref), ("k", kc1[:, :, :T], kc0[:, :, :T], k_ref),
+                          ("v", vc1[:, :, :T], vc0[:, :, :T], v_ref)]:
+        f, p, r = f.double().cpu(), p.double().cpu(), r
+        rl_f, rl_p = float((f - r).norm() / r.norm()), float((p - r).norm() / r.norm())
+        assert rl_f <= 1.25 * rl_p + 1e-4, (name, rl_f, rl_p)
+        scale = r.abs().amax(-1, keepdim=True).clamp_min(1e-6)
+        assert float(((f - r).abs() / scale).max()) <= 1.5 * float(((p - r).abs() / scale).max()) + 2.0 ** -8, name
+    assert bool((kc1[:, :, T:] == 0).all()) and bool((vc1[:, :, T:] == 0).all())
