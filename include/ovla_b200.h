@@ -145,6 +145,15 @@ int ovla_fold_norm_weight(const void* w_dev, const void* gamma_dev, void* out_de
  * mean/std: fp32 [n_towers*3] on the device.  Bit-identical to torchvision's to_tensor + normalize on the host. */
 int ovla_preprocess_frames(const void* frames_u8_dev, int B, int S, int n_towers, const float* mean_dev,
                            const float* std_dev, void* pixel_values_out_dev, void* stream);
+/* PrismaticImageProcessor.apply_transform up to the uint8 frame (processing_prismatic.py:128-135, set-up :70-123):
+ * [letterbox_pad_transform :23-29] -> TVF.resize(bicubic, antialias; on a PIL image = Pillow's ImagingResample) ->
+ * TVF.center_crop, uint8 HWC [B,H,W,3] -> uint8 HWC [B,out_size,out_size,3], bit-identical to Pillow / torchvision.
+ * strategy (`image_resize_strategy`): OVLA_RESIZE_NAIVE stretch to out_size x out_size (openvla-7b), OVLA_RESIZE_CROP
+ * short side -> out_size then center crop, OVLA_RESIZE_LETTERBOX pad to square with fill_{r,g,b} (the reference uses
+ * int(255 * mean) of the last tower) then as OVLA_RESIZE_CROP.  Follow with ovla_preprocess_frames.              */
+enum { OVLA_RESIZE_NAIVE = 0, OVLA_RESIZE_CROP = 1, OVLA_RESIZE_LETTERBOX = 2 };
+int ovla_resize_frames(const void* frames_u8_dev, int B, int H, int W, int strategy, int fill_r, int fill_g, int fill_b,
+                       void* out_u8_dev, int out_size, void* stream);
 /* get_vla_action(center_crop=True) (experiments/robot/openvla_utils.py:155-175, crop_and_resize :81-124): centred
  * square crop of area crop_scale (side sqrt(crop_scale)), bilinear tf.image.crop_and_resize back to out_size x out_size,
  * uint8 HWC [B,H,W,3] -> uint8 HWC [B,out_size,out_size,3] (float32 [0,1] in between, uint8 by scale 255.5 + truncate

@@ -54,6 +54,7 @@ class OpenVLAConfig:
     towers: Tuple[TowerConfig, ...] = (DINOV2_L14_REG4, SIGLIP_SO400M_14)
     image_size: int = 224
     patch: int = 14
+    image_resize_strategy: str = "resize-naive"      # configuration_prismatic.py / openvla-7b's config.json
     text_config: TextConfig = TextConfig()
     pad_token_id: int = 32000
     pad_to_multiple_of: int = 64

@@ -164,6 +164,12 @@ int ovla_attention_tc_qkv(const void* qkv, long long ld, void* out, long long ld
                           int causal, void* stream) {
   return attn_tc_qkv_launch(qkv, ld, out, ldo, B, H, T, head_dim, causal, static_cast<cudaStream_t>(stream));
 }
+int ovla_resize_frames(const void* src_u8, int B, int H, int W, int strategy, int fill_r, int fill_g, int fill_b,
+                       void* dst_u8, int out_size, void* stream) {
+  if (B > 0 && (!src_u8 || !dst_u8)) return set_error("ovla_resize_frames: null buffer");
+  return resize_frames_launch(src_u8, B, H, W, strategy, fill_r, fill_g, fill_b, dst_u8, out_size,
+                              static_cast<cudaStream_t>(stream));
+}
 int ovla_center_crop_frames(const void* src_u8, int B, int H, int W, float crop_scale, void* dst_u8, int out_size,
                             void* stream) {
   if (!src_u8 || !dst_u8) return set_error("ovla_center_crop_frames: null buffer");

@@ -74,6 +74,9 @@ int fold_norm_weight_launch(const void* w, const void* gamma, void* out, long lo
 int flash_attn_launch(const void* Q, const void* K, const void* V, void* O, const long long* strides12, int B, int H,
                       int Tq, int Tk, int head_dim, int causal, cudaStream_t st);
 
+// image.cu -- letterbox / PIL-bicubic resize / center crop of uint8 frames (PrismaticImageProcessor.apply_transform)
+int resize_frames_launch(const void* frames_u8, int B, int H, int W, int strategy, int fill_r, int fill_g, int fill_b,
+                         void* out_u8, int S, cudaStream_t st);
 int center_crop_launch(const void* src_u8, int B, int H, int W, float crop_scale, void* dst_u8, int S, cudaStream_t st);
 
 // attention_tc.cu: causal prefill attention on tcgen05 (head_dim 128)

@@ -44,21 +44,28 @@ class SyntheticProcessor:
     deterministic pseudo-token ids for the prompt and per-tower normalisation of an already 224x224 uint8 frame
     (resize / crop need PIL and are outside the hot path)."""
 
-    def __init__(self, config, prompt_len: int = 31):
+    def __init__(self, config, prompt_len: int = 31, image_processor=None):
+        """`image_processor`: a processing_prismatic.PrismaticImageProcessor -- frames of any size then take the real
+        image transform (letterbox / bicubic resize / center crop / normalize) on the device."""
         self.config = config
         self.prompt_len = prompt_len
+        self.image_processor = image_processor
 
     def __call__(self, prompt: str, image) -> Dict[str, torch.Tensor]:
         img = np.asarray(image)
         c = self.config
-        if img.shape != (c.image_size, c.image_size, 3) or img.dtype != np.uint8:
-            raise ValueError(f"SyntheticProcessor expects a uint8 [{c.image_size},{c.image_size},3] frame")
-        x = torch.from_numpy(img.copy()).permute(2, 0, 1).float() / 255.0
-        stats = [((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
-        if not c.use_fused_vision_backbone:
-            stats = stats[1:]
-        chans = [(x - torch.tensor(m).view(3, 1, 1)) / torch.tensor(s).view(3, 1, 1) for m, s in stats]
-        pixel_values = torch.cat(chans, 0)[None]
+        if self.image_processor is not None:
+            pixel_values = self.image_processor.apply_transform(img)[None]
+        else:
+            if img.shape != (c.image_size, c.image_size, 3) or img.dtype != np.uint8:
+                raise ValueError(f"SyntheticProcessor expects a uint8 [{c.image_size},{c.image_size},3] frame "
+                                 "(pass image_processor= for other sizes)")
+            x = torch.from_numpy(img.copy()).permute(2, 0, 1).float() / 255.0
+            stats = [((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+            if not c.use_fused_vision_backbone:
+                stats = stats[1:]
+            chans = [(x - torch.tensor(m).view(3, 1, 1)) / torch.tensor(s).view(3, 1, 1) for m, s in stats]
+            pixel_values = torch.cat(chans, 0)[None]
         h = np.frombuffer(prompt.encode("utf-8"), dtype=np.uint8).astype(np.int64)
         rng = np.random.default_rng(int(h.sum()) * 7919 + len(h))
         ids = np.concatenate([[1], rng.integers(3, 31744, self.prompt_len - 1)]).astype(np.int64)

@@ -508,3 +508,29 @@ def test_prefill_with_rmsnorm_fused_into_the_gemms(fused_towers, monkeypatch):
     eng.set_option("fuse_norm", 1)
     again = eng.run(ids29, px, od.n_patches + 10, 0, 3, want_hidden=True)
     assert torch.equal(again["hidden"], res[1]["hidden"]) and torch.equal(again["tokens"], res[1]["tokens"])
+
+
+def test_get_vla_action_with_the_device_image_transform():
+    """get_vla_action on a simulator-sized frame (256 x 256) with the PrismaticImageProcessor mirror doing the resize /
+    normalize on the device: same action and embeddings, bit for bit, as feeding the frame the image oracle resized on
+    the host through the plain path (the resize is bit-identical to PIL, the rest is the same engine)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import image_cases as IC
+    from oracle import image_oracle as IO
+    from openvla_probe_b200.openvla_utils import SyntheticProcessor, get_vla_action
+    from openvla_probe_b200.processing_prismatic import openvla_image_processor
+
+    od, pc, W, model, ids, px = _build(B=1, P=9)
+    frame = IC.frame(256, 256, 21)
+    ip = openvla_image_processor(pc)
+    assert ip.image_resize_strategy == "resize-naive" and ip.size == pc.image_size
+    layers = list(range(od.llm_layers + 1))
+    e1, a1 = get_vla_action(model, SyntheticProcessor(pc, prompt_len=9, image_processor=ip), "openvla", {"full_image": frame},
+                            "pick up the bowl", "synthetic", layer_indices=layers, return_embeddings=True)
+    small = IO.transform_u8(frame, "resize-naive", pc.image_size)
+    e2, a2 = get_vla_action(model, SyntheticProcessor(pc, prompt_len=9), "openvla", {"full_image": small},
+                            "pick up the bowl", "synthetic", layer_indices=layers, return_embeddings=True)
+    assert a1.shape == (7,) and np.array_equal(a1, a2)
+    for L in layers:
+        assert np.array_equal(e1[L], e2[L]), L
