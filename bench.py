@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bs1", action="store_true")
     ap.add_argument("--no-probe", action="store_true", help="skip the probe-training leg (configs[3])")
+    ap.add_argument("--no-siglip", action="store_true", help="skip the single-backbone SigLIP bs=64 leg (configs[4])")
     ap.add_argument("--probe-only", action="store_true", help="run only the probe-training leg and print its block")
     ap.add_argument("--probe-kind", default="object", choices=["object", "spatial", "dual"])
     ap.add_argument("--probe-layers", type=int, default=33)
@@ -332,6 +333,70 @@ def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str 
     return out if rank == 0 else None
 
 
+# ----------------------------------------------------------------------------------------------- configs[4] leg
+def siglip_leg(world: int, rank: int, local: int, steps: int, warmup: int, prompt_len: int, batch: int = 64):
+    """BASELINE.json configs[4]: prism-siglip-224px+7b (single SigLIP backbone, 2-layer gelu-mlp projector), bs = 64 per
+    GPU, predict_action + 33-layer capture; same timing rules as the headline (device events, max over ranks; e2e through
+    the public API with host buffers).  Returns the `siglip_bs64` block (rank 0) or None."""
+    import dataclasses
+
+    import torch.distributed as dist
+
+    from openvla_probe_b200 import config as cfgmod, weights
+    from openvla_probe_b200.modeling_prismatic import OpenVLAForActionPrediction
+
+    stats = {"synthetic": {"action": {"q01": np.linspace(-0.9, -0.3, 7).tolist(), "q99": np.linspace(0.4, 1.0, 7).tolist(),
+                                      "mask": [True] * 6 + [False]}}}
+    cfg = dataclasses.replace(cfgmod.siglip_7b(), norm_stats=stats)
+    model = OpenVLAForActionPrediction(cfg, max_batch=batch, max_prompt_len=prompt_len + 1, device=local)
+    weights.bind_random(model, seed=0)
+    ids, px = synthetic_inputs(cfg, batch, prompt_len, seed=11 + rank)
+    ids29 = torch.cat([ids, torch.full((batch, 1), 29871, dtype=torch.int64)], 1)
+    ids_dev, px_dev, px_pin = ids29.cuda(), px.cuda(), px.pin_memory()
+    pool_len = cfg.n_patches + prompt_len
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([e0.elapsed_time(e1), wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / n, float(t[1]) / n
+
+    for _ in range(max(3, warmup)):
+        model.engine.run(ids_dev, px_dev, pool_len, 0, 7)
+    ms_dev, _ = timed(lambda: model.engine.run(ids_dev, px_dev, pool_len, 0, 7), steps)
+    tc = cfg.text_config
+    pool_pin = torch.empty(tc.num_hidden_layers + 1, batch, tc.hidden_size, dtype=torch.float32).pin_memory()
+    api = lambda: model.predict_action_and_capture(ids, unnorm_key="synthetic", layer_indices=list(range(N_LAYERS_CAPTURED)),  # noqa: E731
+                                                   pixel_values=px_pin, pooled_out=pool_pin)
+    api(); api()
+    _, ms_e2e = timed(api, steps)
+    T = cfg.n_patches + prompt_len + 1
+    step_tf = algorithmic_flops_per_action(cfg, T) * batch / (ms_dev * 1e-3) / 1e12
+    out = {"workload": workload_name("siglip-7b", batch, prompt_len), "value": world * batch / (ms_dev / 1e3), "unit": UNIT,
+           "ms_per_step": ms_dev, "steps": steps, "n_gpus": world, "step_tflops_per_gpu": step_tf,
+           "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": UNIT,
+                   "h2d_bytes_per_step": batch * (prompt_len + 1) * 8 + px.numel() * 2,
+                   "d2h_bytes_per_step": (tc.num_hidden_layers + 1) * batch * tc.hidden_size * 4 + batch * 7 * 8}}
+    model.engine.close()
+    del model
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
@@ -485,10 +550,22 @@ def main():
         bs1 = {"p50_ms": statistics.median(lat), "e2e_p50_ms": statistics.median(lat_e2e)}
 
     peaks = load_peaks()
+    # ---- configs[4]: the single-backbone SigLIP model at bs = 64, on the same GPUs, once the headline model is gone
+    siglip_block = None
+    if not args.lite and not args.no_siglip and args.config == "openvla-7b":
+        model.engine.close()
+        del model
+        model = None
+        torch.cuda.empty_cache()
+        try:
+            siglip_block = siglip_leg(world, rank, local, args.steps, args.warmup, P0)
+        except Exception as ex:  # noqa: BLE001 -- recorded, never takes the headline number down
+            siglip_block = {"error": f"{type(ex).__name__}: {ex}"}
     # ---- probe training (configs[3]) on the same GPUs: all ranks take part (NCCL gradient all-reduce at N > 1)
     probe_block = None
     if not args.lite and not args.no_probe:
-        model.engine.close()
+        if model is not None:
+            model.engine.close()
         del model
         torch.cuda.empty_cache()
         try:
@@ -540,6 +617,8 @@ def main():
     }
     if bs1:
         line["bs1_latency"] = bs1
+    if siglip_block:
+        line["siglip_bs64"] = siglip_block
     if probe_block:
         line["probe_training"] = probe_block
     if world == 1 and not args.no_cpu_baseline:

@@ -22,12 +22,26 @@
 // [down + residual]; then [final norm + lm_head].  Summation orders and rounding points are those of the multi-kernel
 // path (norm.cu rmsnorm_split_kernel, gemv.cu, decode_attn.cuh), so both paths return the same bits -- tested.
 #include <algorithm>
+#include <type_traits>
 
 #include "decode_attn.cuh"
 #include "gemm.cuh"
 #include "host_util.h"
 #include "ops.h"
 #include "ptx.cuh"
+
+#ifndef OVLA_MEGA_STAGE_BATCH
+#define OVLA_MEGA_STAGE_BATCH 6      // A/B knobs (tools/decode_trace.py on variant builds)
+#endif
+#ifndef OVLA_MEGA_LDS_GROUP
+#define OVLA_MEGA_LDS_GROUP 8
+#endif
+#ifndef OVLA_MEGA_PIECE_TRACE
+#define OVLA_MEGA_PIECE_TRACE 0      // 1: per-piece (wait, consume) stamps of warp 0 in layer 1 for tools/decode_trace.py
+#endif
+#ifndef OVLA_MEGA_NORM_PREFETCH
+#define OVLA_MEGA_NORM_PREFETCH 0      // measured: no gain (qkv.stage +0.4 us), off
+#endif
 
 namespace ovla {
 
@@ -227,7 +241,9 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           const int col = (c * 32 + lane) * 8;
-          if (col < q) gv[c] = __ldg(reinterpret_cast<const uint4*>(gamma + warp * q + col));
+          // out-of-range chunks load column 0 and are zeroed: unconditional loads keep v / gv in registers (predicated
+          // ones turned them into local-memory arrays), and zeros add nothing to the sum of squares
+          gv[c] = __ldg(reinterpret_cast<const uint4*>(gamma + warp * q + (col < q ? col : 0)));
         }
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
@@ -235,7 +251,8 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
 #pragma unroll
           for (int c = 0; c < 5; ++c) {
             const int col = (c * 32 + lane) * 8;
-            if (col < q) v[m][c] = __ldcg(reinterpret_cast<const uint4*>(xr + col));
+            v[m][c] = __ldcg(reinterpret_cast<const uint4*>(xr + (col < q ? col : 0)));
+            if (col >= q) v[m][c] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
 #pragma unroll
@@ -243,14 +260,11 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
           float sq = 0.f;
 #pragma unroll
           for (int c = 0; c < 5; ++c) {
-            const int col = (c * 32 + lane) * 8;
-            if (col < q) {
-              const uint32_t u[4] = {v[m][c].x, v[m][c].y, v[m][c].z, v[m][c].w};
+            const uint32_t u[4] = {v[m][c].x, v[m][c].y, v[m][c].z, v[m][c].w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16(u[i]);
-                sq += f.x * f.x + f.y * f.y;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = unpack_bf16(u[i]);
+              sq += f.x * f.x + f.y * f.y;
             }
           }
 #pragma unroll
@@ -281,11 +295,30 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
         }
       }
     } else {
-      for (int i = threadIdx.x; i < MB * kv; i += kWarps * 32) {
-        const int m = i / kv, c = i - m * kv;
-        reinterpret_cast<uint4*>(xs)[i] =
-            __ldcg(reinterpret_cast<const uint4*>(src + static_cast<long long>(m < a.M ? m : a.M - 1) * ld + c * 8));
-      }
+      // plain copy: the L2 round trips of a thread's loads overlap (issued six at a time), they do not queue up behind
+      // each other's shared-memory stores (22 KB of SwiGLU output per row: 2.1 -> 0.6 us on the timeline)
+      constexpr int kT = kWarps * 32;
+      const int n = MB * kv, rounds = (n + kT - 1) / kT;
+      auto copy_rounds = [&](auto nb_tag, int r0) {   // NB rounds of kT 16-byte loads, all issued before the first store
+        constexpr int NB = decltype(nb_tag)::value;
+        uint4 v[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int i = min((r0 + j) * kT + static_cast<int>(threadIdx.x), n - 1);   // clamped: every load is valid
+          const int m = i / kv, c = i - m * kv;
+          v[j] = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<long long>(m < a.M ? m : a.M - 1) * ld + c * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int i = (r0 + j) * kT + static_cast<int>(threadIdx.x);
+          if (i < n) reinterpret_cast<uint4*>(xs)[i] = v[j];
+        }
+      };
+      int r0 = 0;
+      for (; r0 + OVLA_MEGA_STAGE_BATCH <= rounds; r0 += OVLA_MEGA_STAGE_BATCH)
+        copy_rounds(std::integral_constant<int, OVLA_MEGA_STAGE_BATCH>{}, r0);
+      for (; r0 + 2 <= rounds; r0 += 2) copy_rounds(std::integral_constant<int, 2>{}, r0);
+      for (; r0 < rounds; ++r0) copy_rounds(std::integral_constant<int, 1>{}, r0);
     }
     cons_sync();
   };
@@ -318,26 +351,59 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
         WsAcc* ac = rsel ? c2 : c1;
         for (int piece = 0; piece < cpr; ++piece) {
           const int slot = static_cast<int>(n_consumed % static_cast<unsigned>(S));
+#if OVLA_MEGA_PIECE_TRACE
           if (ptr_on && ptr_n + 3 <= 500) ptr[ptr_n++] = globaltimer_ns();
+#endif
           mbar_wait(&bars[slot * 2], (n_consumed / static_cast<unsigned>(S)) & 1u);
+#if OVLA_MEGA_PIECE_TRACE
           if (ptr_on && ptr_n + 2 <= 500) ptr[ptr_n++] = globaltimer_ns();
+#endif
           const int k0 = piece * kPiece;
           const int n16 = min(kPiece, K - k0) / 8;
           const uint4* wp = reinterpret_cast<const uint4*>(ring + slot * kPieceBytes);
           const __nv_bfloat16* xk = xs + k0;
           if (!(a.dbg & 1)) {
-#pragma unroll 4
-            for (int i = lane; i < n16; i += 32) {
-              const uint4 wv = wp[i];
+            // kGroup steps of a lane are loaded together and then multiplied (same FMA sequence as a plain loop): with
+            // two consumer warps per scheduler the shared-memory latency of a load-use-load-use chain is exposed.
+            // Measured per layer (tools/decode_trace.py, same box): 91.5 us ungrouped, 88.5 us with groups of 8
+            // (4 and 2 were slower).  What bounds a consumer after that is the SM's one 128 B/clk shared-memory pipe:
+            // per 8 KB piece it carries the bulk-copy write, the weight read and the activation read (1536 clk per
+            // round of 8 warps = 0.8 us, against 1.45 us of HBM time per round) -- keeping the activations in
+            // registers would remove a third of it, but 64 more registers do not fit under the 168 a 9-warp CTA gets.
+            constexpr int kGroup = MB == 1 ? OVLA_MEGA_LDS_GROUP : (MB == 2 ? 2 : 1);
+            const int n_it = n16 >> 5;                      // full steps per lane
+            int it = 0;
+            for (; it + kGroup <= n_it; it += kGroup) {
+              uint4 wv[kGroup], xv[MB][kGroup];
 #pragma unroll
-              for (int m = 0; m < MB; ++m) wstream_fma8(wv, *reinterpret_cast<const uint4*>(xk + m * K + i * 8), ac[m]);
+              for (int j = 0; j < kGroup; ++j) {
+                const int i = lane + 32 * (it + j);
+                wv[j] = wp[i];
+#pragma unroll
+                for (int m = 0; m < MB; ++m) xv[m][j] = *reinterpret_cast<const uint4*>(xk + m * K + i * 8);
+              }
+#pragma unroll
+              for (int j = 0; j < kGroup; ++j) {
+#pragma unroll
+                for (int m = 0; m < MB; ++m) wstream_fma8(wv[j], xv[m][j], ac[m]);
+              }
+            }
+            for (; it * 32 < n16; ++it) {                   // leftover steps, the last one possibly ragged
+              const int i = lane + 32 * it;
+              if (i < n16) {
+                const uint4 wv = wp[i];
+#pragma unroll
+                for (int m = 0; m < MB; ++m) wstream_fma8(wv, *reinterpret_cast<const uint4*>(xk + m * K + i * 8), ac[m]);
+              }
             }
           }
           ++n_consumed;
           // every lane has read the slot: hand it back to the producer
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[slot * 2 + 1]);
+#if OVLA_MEGA_PIECE_TRACE
           if (ptr_on && ptr_n + 1 <= 500) ptr[ptr_n++] = globaltimer_ns();
+#endif
         }
       }
       float acc[MB], acc2[MB];
@@ -389,6 +455,12 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
     ptr_on = ptr != nullptr && layer == 1;
     // The cached K / V rows of this layer do not depend on this step: the CTAs that will run attention pull their head's
     // history into L2 now, so that the attention phase reads L2 instead of queueing behind the weight stream in HBM.
+    // the norm weights this layer's gate/up stage and the next layer's QKV stage (or the final norm) will read: one
+    // 8 KB row each, cold in L2 otherwise -- a full HBM round trip inside a phase where the weight stream is paused
+    if (OVLA_MEGA_NORM_PREFETCH && blockIdx.x == 0 && threadIdx.x == 2 && !(a.dbg & 4)) {
+      l2_prefetch_bulk(l.ln2, static_cast<uint32_t>(D) * 2u);
+      l2_prefetch_bulk(layer + 1 < a.n_layers ? a.layers[layer + 1].ln1 : a.final_norm, static_cast<uint32_t>(D) * 2u);
+    }
     if (threadIdx.x < 2 && !(a.dbg & 4)) {
       for (int p = blockIdx.x; p < a.M * H; p += gridDim.x) {
         const int b = p / H, h = p - b * H;

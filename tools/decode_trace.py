@@ -1,6 +1,8 @@
 """Phase timeline of the persistent bs=1 decode-step kernel (csrc/decode_mega.cu), from %globaltimer stamps of the first
 and last CTA: per phase kind, the mean time spent staging, streaming (linear / attention) and waiting at the grid
-barrier.   OVLA_MEGA_TRACE=1 python tools/decode_trace.py"""
+barrier.   OVLA_MEGA_TRACE=1 python tools/decode_trace.py
+(the per-piece timeline at the end needs a library built with -DOVLA_MEGA_PIECE_TRACE=1:
+ python -m openvla_probe_b200.build -DOVLA_MEGA_PIECE_TRACE=1 --variant=trace; OVLA_B200_LIB=.../libovla_b200_trace.so)"""
 import ctypes as C
 import dataclasses
 import os
