@@ -249,8 +249,42 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------- probe-training leg
+def probe_cpu_baseline(kind: str, batch: int, D: int, K: int, budget_s: float = 15.0):
+    """One layer's probe step as the reference trains it (train_object_probes.py:177-189: nn.Linear, masked
+    BCEWithLogitsLoss with pos_weight, AdamW) through the oracle port's own loss (oracle/probe_oracle.py), fp32, all host
+    threads, on a bounded sample: a few steps of the same batch of 4096 x 4096-d rows."""
+    import torch.nn as nn
+
+    from oracle import probe_oracle as PO
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(batch, D, generator=g)
+    Y = (torch.rand(batch, K, generator=g) < 0.5).to(torch.int8)
+    Y[torch.rand(batch, K, generator=g) < 0.5] = -1
+    model = PO.DualHeadProbe(D, K) if kind == "dual" else nn.Linear(D, K)
+    pw = torch.tensor(1.7) if kind == "dual" else torch.ones(K) * 2.0
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    ts, t_begin = [], time.time()
+    for s in range(8):
+        t0 = time.time()
+        loss, _ = PO.loss_fn(kind, model, X, Y, pw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if s > 0:
+            ts.append(time.time() - t0)
+        if time.time() - t_begin > budget_s and len(ts) >= 2:
+            break
+    sec = sum(ts) / len(ts)
+    return {"value": 1.0 / sec, "unit": "layer-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{len(ts)} timed AdamW steps of one layer's {kind} probe on one batch of {batch} x {D} fp32 rows, "
+                      f"{K} labels ({sec * 1e3:.0f} ms per step), oracle/probe_oracle.py loss (the reference's own torch calls)"}
+
+
 def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str = "object", G: int = 33, batch: int = 4096,
-                       D: int = 4096, K: int = 439, steps: int = 12, warmup: int = 3, chunks: int = 0, comm_sms: int = 16):
+                       D: int = 4096, K: int = 439, steps: int = 12, warmup: int = 3, chunks: int = 0, comm_sms: int = 16,
+                       cpu_baseline: bool = True):
     """BASELINE.json configs[3]: linear (object) probes of all 33 captured layers trained concurrently on synthetic
     4096-d features, multilabel BCE, AdamW; at N > 1 every rank takes its own batch of 4096 rows per layer-step (weak
     scaling, global batch 4096 x N) and the flat [dW | db | stats] gradients go through NCCL all-reduce, chunked and
@@ -330,6 +364,11 @@ def probe_training_leg(world: int, rank: int, local: int, lib, peaks, kind: str 
     }
     del tr
     torch.cuda.empty_cache()
+    if world == 1 and cpu_baseline:
+        try:
+            out["cpu_baseline"] = probe_cpu_baseline(kind, batch, D, K)
+        except Exception as ex:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": f"failed: {type(ex).__name__}: {ex}"}
     return out if rank == 0 else None
 
 
@@ -569,7 +608,8 @@ def main():
         del model
         torch.cuda.empty_cache()
         try:
-            probe_block = probe_training_leg(world, rank, local, lib, peaks, comm_sms=args.probe_comm_sms)
+            probe_block = probe_training_leg(world, rank, local, lib, peaks, comm_sms=args.probe_comm_sms,
+                                             cpu_baseline=not args.no_cpu_baseline)
         except Exception as ex:  # noqa: BLE001 -- recorded, never takes the headline number down
             probe_block = {"error": f"{type(ex).__name__}: {ex}"}
         model = None

@@ -316,6 +316,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ++n_req;
           }
         };
+#ifdef OVLA_DBG_EPI_SKIP      // timing experiment only (no output): is a short-K GEMM bound by its epilogue or by its operand feed?
+        if (false)
+#endif
 #pragma unroll
         for (int i = 0; i < SL; ++i) fetch_res(part + 2 * i);
         float ss0 = 0.f, ss1 = 0.f;   // fused RMSNorm producer: this row's sums of squares, first / second 128 columns
@@ -323,6 +326,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int c = part; c < BN / 32; c += 2) {
           const int col = col0 + c * 32;
           if (col >= shape.N) break;
+#ifdef OVLA_DBG_EPI_SKIP
+          break;
+#endif
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -410,7 +416,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(so + lane * 64 + ((g ^ sw) << 4)) = o4[g];
+#ifndef OVLA_DBG_NO_STORE_FENCE   // timing experiments only
           fence_proxy_async();
+#endif
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmap_out, so, col, row0);
