@@ -348,6 +348,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();          // every lane has read its row: the slot may be refilled
             fetch_res(c + 2 * SL);
           }
+          // Rounding points of the reference's bf16 ops: linear (+ bias) -> [GELU] -> [LayerScale] -> [residual].  After
+          // the first rounding the values travel as packed bf16 pairs: LayerScale and the residual add are single
+          // bf16x2 instructions (bit-identical to fp32 arithmetic + rounding, see mul_bf16x2 / add_bf16x2) -- the
+          // epilogue of a short-K GEMM is bound by its instruction count (profiles/r02q_gemm_epilogue_cost.md).
           uint4 o4[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -355,6 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float x[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+            uint32_t pk[4];
             if (cg < shape.N) {
               if (epi.bias) {
                 const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
@@ -367,44 +372,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
               }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = bf16_round(x[i]);
+              for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
               if (epi.gelu) {
 #pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                  gelu_erf_x2(x[i], x[i + 1]);
-                  x[i] = bf16_round(x[i]);
-                  x[i + 1] = bf16_round(x[i + 1]);
+                for (int i = 0; i < 4; ++i) {
+                  float2 f = unpack_bf16(pk[i]);
+                  gelu_erf_x2(f.x, f.y);
+                  pk[i] = pack_bf16(f.x, f.y);
                 }
               }
               if (epi.scale) {
                 const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
-                const uint32_t sw4[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(sw4[i]);
-                  x[2 * i] = bf16_round(x[2 * i] * f.x);
-                  x[2 * i + 1] = bf16_round(x[2 * i + 1] * f.y);
-                }
+                pk[0] = mul_bf16x2(pk[0], ss.x);
+                pk[1] = mul_bf16x2(pk[1], ss.y);
+                pk[2] = mul_bf16x2(pk[2], ss.z);
+                pk[3] = mul_bf16x2(pk[3], ss.w);
               }
               if (has_res) {
-                const uint32_t rw[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(rw[i]);
-                  x[2 * i] += f.x;
-                  x[2 * i + 1] += f.y;
-                }
+                pk[0] = add_bf16x2(pk[0], rr[g].x);
+                pk[1] = add_bf16x2(pk[1], rr[g].y);
+                pk[2] = add_bf16x2(pk[2], rr[g].z);
+                pk[3] = add_bf16x2(pk[3], rr[g].w);
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
             }
-            o4[g].x = pack_bf16(x[0], x[1]);
-            o4[g].y = pack_bf16(x[2], x[3]);
-            o4[g].z = pack_bf16(x[4], x[5]);
-            o4[g].w = pack_bf16(x[6], x[7]);
+            o4[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             if (epi.ss_out) {   // squares of the values as stored (bf16), in column order
-              const uint32_t ow[4] = {o4[g].x, o4[g].y, o4[g].z, o4[g].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 r = unpack_bf16(ow[i]);
+                const float2 r = unpack_bf16(pk[i]);
                 cs = fmaf(r.x, r.x, cs);
                 cs = fmaf(r.y, r.y, cs);
               }
@@ -633,31 +631,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const __nv_bfloat16* sn = epi.rope_sin + static_cast<long long>(pos) * 64 + half * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float o1[8], o2[8];
+              // the projection output rounded to bf16 (x 1/rms of the fused input norm), packed in column pairs
+              uint32_t a[4], b[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                a[i] = pack_bf16(__uint_as_float(lo[g * 8 + 2 * i]) * rstd, __uint_as_float(lo[g * 8 + 2 * i + 1]) * rstd);
+                b[i] = pack_bf16(__uint_as_float(hi[g * 8 + 2 * i]) * rstd, __uint_as_float(hi[g * 8 + 2 * i + 1]) * rstd);
+              }
+              uint4 w1, w2;
               if (which < 2) {
+                // x cos + rotate_half(x) sin on packed bf16 pairs: every product and the sum rounded to bf16 as the
+                // reference's bf16 ops do (one rounding each, bit-identical to fp32 arithmetic + rounding)
                 const uint4 cu = *reinterpret_cast<const uint4*>(cs + g * 8);
                 const uint4 su = *reinterpret_cast<const uint4*>(sn + g * 8);
                 const uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+                uint32_t r1[4], r2[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 c = unpack_bf16(cw[i]), sI = unpack_bf16(sw[i]);
-                  const float a0 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i]) * rstd), a1 = bf16_round(__uint_as_float(lo[g * 8 + 2 * i + 1]) * rstd);
-                  const float b0 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i]) * rstd), b1 = bf16_round(__uint_as_float(hi[g * 8 + 2 * i + 1]) * rstd);
-                  o1[2 * i] = bf16_round(a0 * c.x) + bf16_round(-b0 * sI.x);
-                  o1[2 * i + 1] = bf16_round(a1 * c.y) + bf16_round(-b1 * sI.y);
-                  o2[2 * i] = bf16_round(b0 * c.x) + bf16_round(a0 * sI.x);
-                  o2[2 * i + 1] = bf16_round(b1 * c.y) + bf16_round(a1 * sI.y);
+                  r1[i] = sub_bf16x2(mul_bf16x2(a[i], cw[i]), mul_bf16x2(b[i], sw[i]));
+                  r2[i] = add_bf16x2(mul_bf16x2(b[i], cw[i]), mul_bf16x2(a[i], sw[i]));
                 }
+                w1 = make_uint4(r1[0], r1[1], r1[2], r1[3]);
+                w2 = make_uint4(r2[0], r2[1], r2[2], r2[3]);
               } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  o1[i] = __uint_as_float(lo[g * 8 + i]) * rstd;
-                  o2[i] = __uint_as_float(hi[g * 8 + i]) * rstd;
-                }
+                w1 = make_uint4(a[0], a[1], a[2], a[3]);
+                w2 = make_uint4(b[0], b[1], b[2], b[3]);
               }
-              uint4 w1, w2;
-              w1.x = pack_bf16(o1[0], o1[1]); w1.y = pack_bf16(o1[2], o1[3]); w1.z = pack_bf16(o1[4], o1[5]); w1.w = pack_bf16(o1[6], o1[7]);
-              w2.x = pack_bf16(o2[0], o2[1]); w2.y = pack_bf16(o2[2], o2[3]); w2.z = pack_bf16(o2[4], o2[5]); w2.w = pack_bf16(o2[6], o2[7]);
               *reinterpret_cast<uint4*>(d1 + g * 8) = w1;
               *reinterpret_cast<uint4*>(d1 + 64 + g * 8) = w2;
             }

@@ -405,4 +405,24 @@ __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
+// Packed bf16 arithmetic with ONE rounding per result.  For two bf16 operands these equal what torch computes for a
+// bf16 tensor op (fp32 arithmetic, then round to bf16) bit for bit: a product of two 8-bit significands is exact in
+// fp32; a sum of two bf16 values is exact in fp32 when their exponents differ by <= 15, and otherwise the small operand
+// lies far below half a bf16 ulp of the large one, so both roundings return the large operand.
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t sub_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 }  // namespace ovla
