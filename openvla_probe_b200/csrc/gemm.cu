@@ -7,6 +7,10 @@
 #include "host_util.h"
 #include "ops.h"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace ovla {
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -167,7 +171,7 @@ int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void
   if (make_tmap_3d_groups(&ta, A, eb, M, K, lda, a_gs, groups, kBM)) return -1;
   if (make_tmap_3d_groups(&tb, W, eb, N, K, ldw, w_gs, groups, bn / cg)) return -1;
   const int num_k = (K + (128 / eb) - 1) / (128 / eb);
-  GemmShape s{M, N, K, 16, 1, num_k, kL2EvictNormal, kL2EvictNormal, groups};
+  GemmShape s{M, N, K, 16, 1, num_k, kL2EvictNormal, kL2EvictNormal, groups, 0, nullptr, 0};
   GemmEpi e = {};
   e.out = out;
   e.ldo = ldo;
@@ -179,6 +183,93 @@ int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void
 }
 
 // Public (library-internal) entry. A: [M,K] lda; W: [N,K] ldw. kind: 0 bf16, 1 tf32(fp32 storage).
+// Rasterisation of the persistent tile loop: (row-tiles per group, column-tiles per super-group, L2 hints of A / W).
+// Overrides, in order: gemm_raster_override (ovla_debug_gemm_raster, used by the sweep tool), the environment
+// (OVLA_GEMM_GROUP, OVLA_GEMM_GROUP_N, OVLA_GEMM_L2 = two letters n/f/l for the A and W loads), the heuristic.
+static int g_raster_override[5] = {-1, -1, -1, -1, -1};
+void gemm_raster_override(int group_m, int group_n, int l2_a, int l2_b, int sync_seg) {
+  g_raster_override[4] = sync_seg;
+  g_raster_override[0] = group_m;
+  g_raster_override[1] = group_n;
+  g_raster_override[2] = l2_a;
+  g_raster_override[3] = l2_b;
+}
+static unsigned long long l2_code(int c) { return c == 2 ? kL2EvictLast : c == 1 ? kL2EvictFirst : kL2EvictNormal; }
+static void gemm_raster_choice(int M, int N, int K, int eb, int bn, int cg, int num_sms, int& group, int& group_n,
+                               unsigned long long& l2_a, unsigned long long& l2_b, int& sync_seg) {
+  static int env_group = -1, env_group_n = -1, env_l2[2] = {-1, -1}, env_sync = -1;
+  if (env_group < 0) {
+    const char* ev = getenv("OVLA_GEMM_GROUP");
+    env_group = (ev && atoi(ev) > 0) ? atoi(ev) : 0;
+    ev = getenv("OVLA_GEMM_GROUP_N");
+    env_group_n = (ev && atoi(ev) > 0) ? atoi(ev) : 0;
+    ev = getenv("OVLA_GEMM_WAVESYNC");
+    env_sync = ev ? atoi(ev) : -1;
+    ev = getenv("OVLA_GEMM_L2");
+    for (int i = 0; i < 2; ++i) {
+      const char c = (ev && ev[0] && ev[1]) ? ev[i] : 'n';
+      env_l2[i] = c == 'l' ? 2 : c == 'f' ? 1 : 0;
+    }
+  }
+  // Heuristic (profiles/r02t_gemm_raster.md).  A persistent grid drifts out of phase: CTAs that share an operand tile
+  // read it up to a whole tile duration apart, the L2 (whose useful capacity under this streaming load is a few tens of
+  // MB) has dropped it by then and DRAM serves every reader.  Multi-wave problems therefore align their producers
+  // (sync_seg K blocks apart: once per tile up to K = 6144, ~60 K blocks beyond), which cut the DRAM reads of the four
+  // Llama prefill GEMMs by 2-2.6x and their time by 4-10 %.  With aligned waves: N <= 4096 keeps W resident under
+  // narrow row groups (and, for long K, half of the columns at a time); wider N keeps a 16-row-tile activation slab.
+  const int num_k = (K + (128 / eb) - 1) / (128 / eb);
+  const long long tiles = ((M + 128LL * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+  const bool multi_wave = M >= 8192 && tiles >= 2LL * (num_sms / cg);
+  group = (N <= 4096 && K <= 4096) ? 8 : 16;
+  group_n = 0;
+  sync_seg = 0;
+  if (multi_wave && K >= 2048) {
+    const int parts = (num_k + 95) / 96 > 1 ? (num_k + 32) / 64 : 1;
+    sync_seg = (num_k + parts - 1) / parts;
+    if (N <= 4096) {
+      group = K <= 4096 ? 2 : 4;
+      if (K > 4096) group_n = 8;
+    }
+  }
+  int la = 0, lb = 0;
+  if (env_group > 0) group = env_group;
+  if (env_group_n > 0) group_n = env_group_n;
+  if (env_l2[0] > 0) la = env_l2[0];
+  if (env_l2[1] > 0) lb = env_l2[1];
+  if (g_raster_override[0] > 0) group = g_raster_override[0];
+  if (g_raster_override[1] >= 0) group_n = g_raster_override[1];
+  if (g_raster_override[2] >= 0) la = g_raster_override[2];
+  if (g_raster_override[3] >= 0) lb = g_raster_override[3];
+  l2_a = l2_code(la);
+  l2_b = l2_code(lb);
+  if (env_sync >= 0) sync_seg = env_sync;
+  if (g_raster_override[4] >= 0) sync_seg = g_raster_override[4];
+}
+
+// two zero-initialised words per (device, stream) for the wave alignment of gemm_tcgen05_kernel: launches on one stream
+// run one after the other and each leaves the words zeroed; allocated outside stream capture only
+static unsigned int* gemm_sync_words(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned int*> words;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = words.find({dev, st});
+  if (it != words.end()) return it->second;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  unsigned int* p = nullptr;
+  if (cudaMalloc(&p, 256) != cudaSuccess || cudaMemset(p, 0, 256) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  words[{dev, st}] = p;
+  return p;
+}
+
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int mode, int kind,
                 const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream, SplitKWs ws) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm: empty shape M=%d N=%d K=%d", M, N, K);
@@ -221,23 +312,12 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (mode == kModeSwiGLU && bn < 64) return set_error("gemm: SwiGLU needs bn >= 64");
   if (mode == kModeQkvRope && bn < 128) { bn = 128; cg = 1; }  // a tile must hold whole 128-wide heads
   if (epi.ss_out && bn < 128) { bn = 128; cg = 1; }            // a thread must own whole (128-column group, parity) slots
-  // rasterisation group (tools/gemm_group_sweep.py, profiles/r01_gemm_group_sweep.jsonl): 16 row-tiles keep the
-  // activation slab of a group L2-resident while the weights stream; narrow, short-K problems prefer 8
-  static int g_group = -1, g_split = -2;
-  if (g_group < 0) { const char* ev = getenv("OVLA_GEMM_GROUP"); g_group = (ev && atoi(ev) > 0) ? atoi(ev) : 0; }
+  // rasterisation (tools/gemm_raster_sweep.py, profiles/r02s_gemm_raster.md): see gemm_raster_choice
+  static int g_split = -2;
   if (g_split == -2) { const char* ev = getenv("OVLA_SPLITK"); g_split = ev ? atoi(ev) : -1; }  // -1 auto, 0/1 off, n forced
-  const int group = g_group > 0 ? g_group : ((N <= 4096 && K <= 4096) ? 8 : 16);
-
-  // L2 eviction hints: OVLA_GEMM_L2 = two letters for the A and W tile loads, n(ormal) / f(irst) / l(ast)
-  static unsigned long long g_l2[2] = {0, 0};
-  if (!g_l2[0]) {
-    const char* ev = getenv("OVLA_GEMM_L2");
-    for (int i = 0; i < 2; ++i) {
-      const char c = (ev && ev[0] && ev[1]) ? ev[i] : 'n';
-      g_l2[i] = c == 'l' ? kL2EvictLast : c == 'f' ? kL2EvictFirst : kL2EvictNormal;
-    }
-  }
-  const unsigned long long l2_a = g_l2[0], l2_b = g_l2[1];
+  int group, group_n, sync_seg;
+  unsigned long long l2_a, l2_b;
+  gemm_raster_choice(M, N, K, eb, bn, cg, num_sms, group, group_n, l2_a, l2_b, sync_seg);
 
   // split-K for the small-M weight-streaming shapes (see splitk.cu)
   const int num_k = (K + (128 / eb) - 1) / (128 / eb);
@@ -275,7 +355,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
   if (make_tmap_2d(&tb, W, eb, N, K, ldw, bn / cg)) return -1;
   if (split >= 2) {
     const int kps = (num_k + split - 1) / split;
-    GemmShape s{M, N, K, group, split, kps, l2_a, l2_b};
+    GemmShape s{M, N, K, group, split, kps, l2_a, l2_b, 1, group_n, nullptr, 0};
     GemmEpi pe = {};
     pe.out = ws.ptr;
     pe.ldo = N;
@@ -284,7 +364,8 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
     else OVLA_TRY((dispatch_tile<kModePartial, kKindTf32>(bn, cg, ta, tb, ta, ta, s, pe, num_sms, stream)));
     return splitk_epilogue_launch(mode, ws.ptr, 1LL * M * N, N, split, M, N, epi, stream);
   }
-  GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b};
+  GemmShape s{M, N, K, group, 1, num_k, l2_a, l2_b, 1, group_n, nullptr, 0};
+  if (sync_seg > 0 && (s.sync = gemm_sync_words(stream)) != nullptr) s.sync_seg = sync_seg;
   if (kind == kKindBf16 && (mode == kModeBf16 || mode == kModeSwiGLU)) {
     // epilogue through shared memory + TMA (OVLA_GEMM_TMA_EPI=0 keeps the direct per-row stores); needs 16-byte
     // aligned bases and pitches, otherwise the direct path runs

@@ -94,6 +94,14 @@ struct GemmShape {
   // > 1: `groups` independent problems of the same shape in one launch (the probes of all captured layers): A and W
   // are 3-D tensor maps (k, row, group) whose row boxes clip at the group's own M / N, tiles are numbered group-major
   int groups;
+  // rasterisation super-group (column-tiles): the row groups sweep `group_n` column-tiles at a time, so that a W slab
+  // of group_n * BN rows stays L2-resident while the activations stream; 0 = all column-tiles (one super-group)
+  int group_n;
+  // wave alignment (long-K problems): the TMA producers of all CTAs meet every `sync_seg` K blocks (bounded skew), so
+  // that CTAs that share operand tiles fetch them from L2 at the same time and one DRAM read serves them all.
+  // sync = two zero-initialised words (arrivals, exits) that the last CTA to leave zeroes again; nullptr = off
+  unsigned int* sync;
+  int sync_seg;
 };
 
 #ifndef OVLA_EPI_SLOTS
@@ -123,16 +131,26 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-// Tile rasterisation: groups of G row-tiles sweep all column-tiles, so that a wave of concurrent CTAs touches a
-// near-square block of the output and both operands are re-used from L2.
-__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int& mb, int& nb) {
-  const int per_group = G * num_n;
+// Tile rasterisation: groups of G row-tiles sweep the column-tiles of a super-group of NC column-tiles (NC = 0: all of
+// them), so that a wave of concurrent CTAs touches a near-square block of the output and both operands are re-used
+// from L2.  Which operand stays resident across waves is the launcher's choice: a wide G keeps the activation slab
+// [G * tile rows, K] while W streams; a narrow G with NC column-tiles keeps the W slab [NC * BN, K] while the
+// activations stream (once per super-group).
+__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int NC, int& mb, int& nb) {
+  int first_n = 0, ncs = num_n;
+  if (NC > 0 && NC < num_n) {
+    const int sg = t / (num_m * NC);
+    first_n = sg * NC;
+    ncs = min(NC, num_n - first_n);
+    t -= sg * num_m * NC;
+  }
+  const int per_group = G * ncs;
   const int g = t / per_group;
   const int first_m = g * G;
   const int gsz = min(G, num_m - first_m);
   const int in_g = t - g * per_group;
   mb = first_m + in_g % gsz;
-  nb = in_g / gsz;
+  nb = first_n + in_g / gsz;
 }
 
 template <int BN, int CG, int MODE, int KIND>
@@ -199,15 +217,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // wave alignment: segment g of the launch (tile iteration x segments per tile) starts once every CTA has issued
+      // the loads of segment g - 1; a CTA that runs out of tiles hands in its remaining arrivals at once
+      unsigned int* const sync = shape.sync;
+      const int segs_per_tile = sync ? (num_k + shape.sync_seg - 1) / shape.sync_seg : 0;
+      unsigned int seg_done = 0;
+      bool gave_up = false;
       for (int t = worker; t < num_tiles; t += num_workers) {
         int mb, nb;
         const int outer = t / tiles_mn;
         const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
-        gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
+        gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, shape.group_n, mb, nb);
         const int row_a = mb * kTileM + static_cast<int>(cta_rank) * kBM;
         const int row_b = nb * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
+        int next_sync = kb0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (sync && kb == next_sync) {
+            if (kb != kb0 || seg_done) {
+              if (kb != kb0) { red_add_relaxed_gpu(sync, 1u); ++seg_done; }
+              const unsigned int want = seg_done * gridDim.x;
+              if (!gave_up && ld_relaxed_gpu(sync) < want) {
+                // the alignment is a timing aid only: if part of the grid is not resident (SMs held by another
+                // kernel), stop waiting after ~4 M cycles and never wait again -- no CTA can block another for good
+                const long long t0 = clock64();
+                while (ld_relaxed_gpu(sync) < want) {
+                  if (clock64() - t0 > (4LL << 20)) { gave_up = true; break; }
+                }
+              }
+            }
+            next_sync += shape.sync_seg;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
@@ -231,6 +271,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d_pair_hint(&tmap_b, &full_bar[stage], sb, kb * kKElems, row_b, shape.l2_b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (sync) { red_add_relaxed_gpu(sync, 1u); ++seg_done; }   // last segment of this tile issued
+      }
+      if (sync) {
+        const unsigned int total = static_cast<unsigned int>((num_tiles + num_workers - 1) / num_workers) * segs_per_tile;
+        if (seg_done < total) red_add_relaxed_gpu(sync, total - seg_done);
+        if (atom_add_relaxed_gpu(sync + 1, 1u) == gridDim.x - 1) {   // everyone is past its last wait: clean up
+          st_relaxed_gpu(sync, 0u);
+          st_relaxed_gpu(sync + 1, 0u);
         }
       }
     }
@@ -281,7 +330,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int mb, nb;
       const int outer = t / tiles_mn;
       const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
-      gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, mb, nb);
+      gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, shape.group_n, mb, nb);
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
       const bool row_ok = row < shape.M;
       float rstd = 1.f;
