@@ -227,7 +227,7 @@ static void gemm_raster_choice(int M, int N, int K, int eb, int bn, int cg, int 
     const int parts = (num_k + 95) / 96 > 1 ? (num_k + 32) / 64 : 1;
     sync_seg = (num_k + parts - 1) / parts;
     if (N <= 4096) {
-      group = K <= 4096 ? 2 : 4;
+      group = 2;
       if (K > 4096) group_n = 8;
     }
   }

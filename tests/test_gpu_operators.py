@@ -311,6 +311,53 @@ def test_gemm_inplace_residual_ragged_multi_tile_bit_exact(L, M, N, K):
             assert bool((buf[M:] == 7.0).all()), (bn, cg, rep, "stored outside [0, M)")
 
 
+@pytest.mark.parametrize("M,N,K,mode", [(8192 + 77, 4096, 4096, 0), (9000, 1152, 4304, 0), (8448, 2816, 2048, 1),
+                                          (8300, 4096, 5632, 0)])
+def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K, mode):
+    """Round 2: multi-wave GEMMs (M >= 8192) align the TMA producers of the persistent grid at tile / mid-tile boundaries
+    through two global counters (gemm.cuh `GemmShape::sync`) and walk the tiles in row groups inside column
+    super-groups.  Neither may change a bit of the output: every (group, super-group, alignment distance) -- forced
+    through ovla_debug_gemm_raster -- must equal the un-aligned, single-super-group launch, for ragged M, an N that is
+    not a multiple of the tile, the in-place residual epilogue and SwiGLU; the counters must be left clean so that
+    launches of different grids follow each other on one stream; nothing may be stored outside [0, M)."""
+    _lib, lib = L
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, generator=g, device="cuda") * 0.5)
+    W = bf(torch.randn(N, K, generator=g, device="cuda") * 0.03)
+    n_out = N // 2 if mode == 1 else N
+    X = bf(torch.randn(M, n_out, generator=g, device="cuda"))
+
+    def call(buf, bn=0, cg=0):
+        epi = _lib.GemmEpilogue()
+        if mode == 0:
+            epi.resid_bf16, epi.ld_resid = buf.data_ptr(), n_out
+        _lib.check(lib.ovla_gemm(P(A), K, P(W), K, M, N, K, mode, 0, P(buf), n_out, C.byref(epi), bn, cg, None))
+
+    try:
+        lib.ovla_debug_gemm_raster(16, 0, 0, 0, 0)       # round-1 rasterisation, no alignment
+        ref = X.clone()
+        call(ref)
+        torch.cuda.synchronize()
+        if mode == 0:
+            want = (A.float() @ W.float().t()).bfloat16().float() + X.float()
+            ok, e = close_bf16(ref, want, ulps=3.0)
+            assert ok, e
+        num_k = (K + 63) // 64
+        cfgs = [(-1, -1, -1, -1, -1), (2, 0, 0, 0, num_k), (2, 3, 0, 0, 7), (5, 2, 1, 2, 1), (16, 1, 0, 0, num_k // 2),
+                (1, 0, 2, 0, 10 ** 6), (3, 1000, 0, 0, 0)]
+        for ci, cfg in enumerate(cfgs):
+            lib.ovla_debug_gemm_raster(*cfg)
+            for bn, cg in [(0, 0), (128, 1)] if ci % 2 == 0 else [(0, 0)]:
+                buf = torch.full((M + 64, n_out), 7.0, dtype=torch.bfloat16, device="cuda")
+                buf[:M].copy_(X)
+                call(buf[:M], bn, cg)
+                torch.cuda.synchronize()
+                assert int((buf[:M] != ref).sum()) == 0, (cfg, bn, cg)
+                assert bool((buf[M:] == 7.0).all()), (cfg, bn, cg, "stored outside [0, M)")
+    finally:
+        lib.ovla_debug_gemm_raster(-1, -1, -1, -1, -1)
+
+
 @pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])
 def test_decode_rope_attention_and_cache_append(L, B, ctx):
     """Fused RoPE + KV append + 1-query attention == oracle llama attention step with a KV cache."""
