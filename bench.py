@@ -75,9 +75,9 @@ def ncu_traffic():
             if "<256, 2, 1, 0>" in r[ik]:
                 return (float(r[ir]) + float(r[iw])) * 1e9, (
                     "bytes per launch of gemm_tcgen05_kernel<256,2,SwiGLU> (M=72448 N=22016 K=4096; algorithmic 2.37e9: "
-                    "A 0.59 + W 0.18 + out 1.59 GB) from profiles/" + os.path.basename(path) + "; the excess is A/W tile "
-                    "re-reads that miss L2, at ~1.1-1.4 TB/s -- about a fifth of HBM peak, not the limiter of this "
-                    "tensor-bound kernel (L2 eviction hints did not change its time: profiles/r01_gemm_l2_hint_sweep.jsonl)")
+                    "A 0.59 + W 0.18 + out 1.59 GB) from profiles/" + os.path.basename(path) + "; was 8.0e9 before the "
+                    "producers of the persistent grid were aligned (profiles/r02t_gemm_raster.md); what is left is W "
+                    "re-read once per 16-row-tile group (18 x 0.18 GB): a wider activation slab falls out of the L2")
     except (OSError, ValueError, IndexError):
         pass
     return None, "no ncu capture in profiles/"

@@ -37,8 +37,9 @@ int ovla_profile_collect(long long* launches, double* ms, double* flops, double*
 /* Measurement knob (tools/gemm_raster_sweep.py): override the tile rasterisation of every following ovla_gemm launch
  * of this process: row-tiles per group, column-tiles per super-group (0 = all), L2 eviction hint of the A / W tile
  * loads (0 normal, 1 evict-first, 2 evict-last), K blocks between two alignment points of the CTAs' TMA producers
- * (0 = off); a negative value returns that knob to the launcher's heuristic.                                      */
-void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg);
+ * (0 = off), serpentine column order of alternate row groups (0 / 1); a negative value returns that knob to the
+ * launcher's heuristic.                                                                                          */
+void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine);
 
 /* ------------------------------------------------------------------ operators (device pointers)
  * Building blocks of PrismaticForConditionalGeneration.forward (prismatic/extern/hf/modeling_prismatic.py:291-447),

@@ -41,8 +41,8 @@ int ovla_abi_version(void) { return OVLA_ABI_VERSION; }
 const char* ovla_last_error(void) { return last_error(); }
 long long ovla_launch_count(void) { return launch_count(); }
 void ovla_reset_launch_count(void) { reset_launch_count(); }
-void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg) {
-  gemm_raster_override(group_m, group_n, l2_a, l2_b, sync_seg);
+void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine) {
+  gemm_raster_override(group_m, group_n, l2_a, l2_b, sync_seg, serpentine);
 }
 void ovla_profile_enable(int on) { prof_enable(on != 0); }
 int ovla_profile_collect(long long* launches, double* ms, double* flops, double* bytes) {

@@ -186,9 +186,10 @@ int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void
 // Rasterisation of the persistent tile loop: (row-tiles per group, column-tiles per super-group, L2 hints of A / W).
 // Overrides, in order: gemm_raster_override (ovla_debug_gemm_raster, used by the sweep tool), the environment
 // (OVLA_GEMM_GROUP, OVLA_GEMM_GROUP_N, OVLA_GEMM_L2 = two letters n/f/l for the A and W loads), the heuristic.
-static int g_raster_override[5] = {-1, -1, -1, -1, -1};
-void gemm_raster_override(int group_m, int group_n, int l2_a, int l2_b, int sync_seg) {
+static int g_raster_override[6] = {-1, -1, -1, -1, -1, -1};
+void gemm_raster_override(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine) {
   g_raster_override[4] = sync_seg;
+  g_raster_override[5] = serpentine;
   g_raster_override[0] = group_m;
   g_raster_override[1] = group_n;
   g_raster_override[2] = l2_a;
@@ -223,12 +224,15 @@ static void gemm_raster_choice(int M, int N, int K, int eb, int bn, int cg, int 
   group = (N <= 4096 && K <= 4096) ? 8 : 16;
   group_n = 0;
   sync_seg = 0;
+  bool serp = false;
   if (multi_wave && K >= 2048) {
     const int parts = (num_k + 95) / 96 > 1 ? (num_k + 32) / 64 : 1;
     sync_seg = (num_k + parts - 1) / parts;
     if (N <= 4096) {
       group = 2;
       if (K > 4096) group_n = 8;
+    } else {
+      serp = true;   // the W tiles a row group used last are the first ones the next group needs (-5 % DRAM reads)
     }
   }
   int la = 0, lb = 0;
@@ -244,6 +248,8 @@ static void gemm_raster_choice(int M, int N, int K, int eb, int bn, int cg, int 
   l2_b = l2_code(lb);
   if (env_sync >= 0) sync_seg = env_sync;
   if (g_raster_override[4] >= 0) sync_seg = g_raster_override[4];
+  if (g_raster_override[5] >= 0) serp = g_raster_override[5] != 0;
+  if (serp) group_n |= kRasterSerpentine;
 }
 
 // two zero-initialised words per (device, stream) for the wave alignment of gemm_tcgen05_kernel: launches on one stream

@@ -85,6 +85,8 @@ __device__ __forceinline__ float fused_norm_rstd(const GemmEpi& epi, int row, bo
   return rsqrtf(ss * epi.ss_inv_k + epi.ss_eps);
 }
 
+static constexpr int kRasterSerpentine = 1 << 30;  // or-ed into GemmShape::group_n
+
 struct GemmShape {
   int M, N, K;  // N = rows of W (pre-epilogue output columns); K in elements
   int group_m;  // rasterisation group size (row-tiles)
@@ -137,6 +139,8 @@ struct GemmCfg {
 // [G * tile rows, K] while W streams; a narrow G with NC column-tiles keeps the W slab [NC * BN, K] while the
 // activations stream (once per super-group).
 __device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int NC, int& mb, int& nb) {
+  const bool serp = (NC >> 30) & 1;
+  NC &= ~(1 << 30);
   int first_n = 0, ncs = num_n;
   if (NC > 0 && NC < num_n) {
     const int sg = t / (num_m * NC);
@@ -150,7 +154,10 @@ __device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, in
   const int gsz = min(G, num_m - first_m);
   const int in_g = t - g * per_group;
   mb = first_m + in_g % gsz;
-  nb = first_n + in_g / gsz;
+  const int c = in_g / gsz;
+  // serpentine (bit 30 of NC, kRasterSerpentine): odd row groups sweep the columns backwards, so the W tiles the
+  // previous group used last -- still in L2 -- are the first ones this group needs
+  nb = first_n + ((serp && (g & 1)) ? ncs - 1 - c : c);
 }
 
 template <int BN, int CG, int MODE, int KIND>

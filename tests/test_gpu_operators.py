@@ -316,7 +316,7 @@ def test_gemm_inplace_residual_ragged_multi_tile_bit_exact(L, M, N, K):
 def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K, mode):
     """Round 2: multi-wave GEMMs (M >= 8192) align the TMA producers of the persistent grid at tile / mid-tile boundaries
     through two global counters (gemm.cuh `GemmShape::sync`) and walk the tiles in row groups inside column
-    super-groups.  Neither may change a bit of the output: every (group, super-group, alignment distance) -- forced
+    super-groups, optionally serpentine.  None may change a bit of the output: every (group, super-group, alignment distance, order) -- forced
     through ovla_debug_gemm_raster -- must equal the un-aligned, single-super-group launch, for ragged M, an N that is
     not a multiple of the tile, the in-place residual epilogue and SwiGLU; the counters must be left clean so that
     launches of different grids follow each other on one stream; nothing may be stored outside [0, M)."""
@@ -334,7 +334,7 @@ def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K,
         _lib.check(lib.ovla_gemm(P(A), K, P(W), K, M, N, K, mode, 0, P(buf), n_out, C.byref(epi), bn, cg, None))
 
     try:
-        lib.ovla_debug_gemm_raster(16, 0, 0, 0, 0)       # round-1 rasterisation, no alignment
+        lib.ovla_debug_gemm_raster(16, 0, 0, 0, 0, 0)    # round-1 rasterisation, no alignment
         ref = X.clone()
         call(ref)
         torch.cuda.synchronize()
@@ -343,8 +343,8 @@ def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K,
             ok, e = close_bf16(ref, want, ulps=3.0)
             assert ok, e
         num_k = (K + 63) // 64
-        cfgs = [(-1, -1, -1, -1, -1), (2, 0, 0, 0, num_k), (2, 3, 0, 0, 7), (5, 2, 1, 2, 1), (16, 1, 0, 0, num_k // 2),
-                (1, 0, 2, 0, 10 ** 6), (3, 1000, 0, 0, 0)]
+        cfgs = [(-1, -1, -1, -1, -1, -1), (2, 0, 0, 0, num_k, 1), (2, 3, 0, 0, 7, 1), (5, 2, 1, 2, 1, 0), (16, 1, 0, 0, num_k // 2, 1),
+                (1, 0, 2, 0, 10 ** 6, 0), (3, 1000, 0, 0, 0, 1)]
         for ci, cfg in enumerate(cfgs):
             lib.ovla_debug_gemm_raster(*cfg)
             for bn, cg in [(0, 0), (128, 1)] if ci % 2 == 0 else [(0, 0)]:
@@ -355,7 +355,7 @@ def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K,
                 assert int((buf[:M] != ref).sum()) == 0, (cfg, bn, cg)
                 assert bool((buf[M:] == 7.0).all()), (cfg, bn, cg, "stored outside [0, M)")
     finally:
-        lib.ovla_debug_gemm_raster(-1, -1, -1, -1, -1)
+        lib.ovla_debug_gemm_raster(-1, -1, -1, -1, -1, -1)
 
 
 @pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])

@@ -21,18 +21,17 @@ SHAPES_VIT = {"dino_qkv": (66816, 3072, 1024, 0, False, False), "dino_proj": (66
               "sig_qkv": (65536, 3456, 1152, 0, False, False), "sig_fc1": (65536, 4304, 1152, 0, False, True),
               "sig_fc2": (65536, 1152, 4304, 0, True, False), "proj_fc1": (65536, 8704, 2176, 0, False, True),
               "proj_fc2": (65536, 4096, 8704, 0, False, True)}
-# (G, NC, l2_a, l2_b, sync); NC = 0: all column-tiles; hints 0 normal / 1 evict-first / 2 evict-last; sync = K blocks
+# (G, NC, l2_a, l2_b, sync, serpentine); NC = 0: all column-tiles; hints 0 normal / 1 evict-first / 2 evict-last; sync = K blocks
 # between two alignment points of the producers (0 = off, >= K/64: once per tile); -1 = the launcher's heuristic
-AUTO = (-1, -1, -1, -1, -1)
-CONFIGS_LLAMA = {
-    "qkv": [(16, 0, 0, 0, 0), AUTO, (12, 0, 0, 0, 64), (20, 0, 0, 0, 64), (16, 24, 0, 0, 64), (8, 16, 0, 0, 64), (4, 16, 0, 0, 64),
-            (2, 16, 0, 0, 64), (16, 0, 2, 0, 64)],
-    "o": [(8, 0, 0, 0, 0), AUTO, (1, 0, 0, 0, 64), (3, 0, 0, 0, 64), (4, 0, 0, 0, 64), (2, 8, 0, 0, 64), (2, 0, 0, 2, 64)],
-    "gate_up": [(16, 0, 0, 0, 0), AUTO, (12, 0, 0, 0, 64), (20, 0, 0, 0, 64), (16, 43, 0, 0, 64), (16, 22, 0, 0, 64), (16, 0, 2, 0, 64)],
-    "down": [(16, 0, 0, 0, 0), AUTO, (4, 8, 0, 0, 86), (4, 8, 0, 0, 172), (3, 8, 0, 0, 58), (6, 8, 0, 0, 58), (2, 8, 0, 0, 58),
-             (8, 4, 0, 0, 58), (4, 4, 0, 0, 58), (5, 8, 0, 0, 58), (4, 8, 0, 2, 58), (4, 6, 0, 0, 58)],
+AUTO = (-1, -1, -1, -1, -1, -1)
+CONFIGS_LLAMA = {   # (G, NC, l2_a, l2_b, sync, serpentine)
+    "qkv": [(16, 0, 0, 0, 0, 0), AUTO, (16, 0, 0, 0, 64, 1), (20, 0, 0, 0, 64, 1), (24, 0, 0, 0, 64, 1), (12, 0, 0, 0, 64, 1),
+            (2, 16, 0, 0, 64, 0), (2, 16, 0, 0, 64, 1)],
+    "o": [(8, 0, 0, 0, 0, 0), AUTO],
+    "gate_up": [(16, 0, 0, 0, 0, 0), AUTO, (16, 0, 0, 0, 64, 1), (20, 0, 0, 0, 64, 1), (24, 0, 0, 0, 64, 1), (12, 0, 0, 0, 64, 1)],
+    "down": [(16, 0, 0, 0, 0, 0), AUTO, (2, 8, 0, 0, 58, 1), (3, 0, 0, 0, 58, 1), (4, 0, 0, 0, 58, 1)],
 }
-VIT_GRID = [(8, 0, 0, 0, 0), (16, 0, 0, 0, 0), AUTO, (8, 0, 0, 0, 999), (16, 0, 0, 0, 999), (2, 0, 0, 0, 999), (4, 0, 0, 0, 999)]
+VIT_GRID = [(8, 0, 0, 0, 0, 0), (16, 0, 0, 0, 0, 0), AUTO, (8, 0, 0, 0, 999, 0), (16, 0, 0, 0, 999, 0), (2, 0, 0, 0, 999, 0), (4, 0, 0, 0, 999, 0)]
 CONFIGS_VIT = {n: VIT_GRID for n in SHAPES_VIT}
 SHAPES, CONFIGS = dict(SHAPES_LLAMA), dict(CONFIGS_LLAMA)
 if os.environ.get("RASTER_SET") == "vit":
@@ -90,7 +89,7 @@ def main():
             algo = 2.0 * (M * K + N * K + M * n_out * (2 if resid else 1))
             rd, wr = m.get("dram__bytes_read.sum", 0), m.get("dram__bytes_write.sum", 0)
             unit_fix = 1.0
-            print(json.dumps({"shape": n, "G": c[0], "NC": c[1], "l2_a_w": "anfl"[c[2] + 1] + "anfl"[c[3] + 1], "sync": c[4],
+            print(json.dumps({"shape": n, "G": c[0], "NC": c[1], "l2_a_w": "anfl"[c[2] + 1] + "anfl"[c[3] + 1], "sync": c[4], "serp": c[5],
                               "dram_read_gb": round(rd * unit_fix / 1e9, 2), "dram_write_gb": round(wr / 1e9, 2),
                               "x_algorithmic": round((rd + wr) / algo, 2), "algorithmic_gb": round(algo / 1e9, 2),
                               "l2_hit_pct": round(m.get("lts__t_sector_hit_rate.pct", -1), 1),
@@ -119,7 +118,7 @@ def main():
     print("bit-identical outputs over all configs", flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # warm the box into its power-capped state
-    lib.ovla_debug_gemm_raster(-1, -1, -1, -1, -1)
+    lib.ovla_debug_gemm_raster(*AUTO)
     for _ in range(40):
         for name in SHAPES: run(name)
     torch.cuda.synchronize()
@@ -134,7 +133,7 @@ def main():
                 for _ in range(reps): run(name)
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
-                line = json.dumps({"round": rnd, "shape": name, "G": c[0], "NC": c[1], "l2_a_w": "anfl"[c[2] + 1] + "anfl"[c[3] + 1], "sync": c[4],
+                line = json.dumps({"round": rnd, "shape": name, "G": c[0], "NC": c[1], "l2_a_w": "anfl"[c[2] + 1] + "anfl"[c[3] + 1], "sync": c[4], "serp": c[5],
                                    "us": round(ms * 1e3, 1), "tflops": round(fl / ms / 1e9, 1)})
                 print(line, flush=True)
                 if out: out.write(line + "\n"); out.flush()
