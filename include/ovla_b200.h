@@ -40,6 +40,9 @@ int ovla_profile_collect(long long* launches, double* ms, double* flops, double*
  * (0 = off), serpentine column order of alternate row groups (0 / 1); a negative value returns that knob to the
  * launcher's heuristic.                                                                                          */
 void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine);
+/* HOST-side evaluation of the GEMM kernel's tile walk (no GPU needed): tile t = 0 .. num_m * num_n - 1 of a problem of
+ * num_m x num_n output tiles is (mb_out[t], nb_out[t]) for the given rasterisation knobs.                        */
+int ovla_debug_gemm_tile_order(int num_m, int num_n, int group_m, int group_n, int serpentine, int* mb_out, int* nb_out);
 
 /* ------------------------------------------------------------------ operators (device pointers)
  * Building blocks of PrismaticForConditionalGeneration.forward (prismatic/extern/hf/modeling_prismatic.py:291-447),

@@ -41,6 +41,11 @@ int ovla_abi_version(void) { return OVLA_ABI_VERSION; }
 const char* ovla_last_error(void) { return last_error(); }
 long long ovla_launch_count(void) { return launch_count(); }
 void ovla_reset_launch_count(void) { reset_launch_count(); }
+int ovla_debug_gemm_tile_order(int num_m, int num_n, int group_m, int group_n, int serpentine, int* mb_out, int* nb_out) {
+  if (num_m <= 0 || num_n <= 0 || group_m <= 0 || group_n < 0 || !mb_out || !nb_out) return set_error("tile order: bad arguments");
+  for (int t = 0; t < num_m * num_n; ++t) gemm_tile_coords_host(t, num_m, num_n, group_m, group_n, serpentine, mb_out + t, nb_out + t);
+  return 0;
+}
 void ovla_debug_gemm_raster(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine) {
   gemm_raster_override(group_m, group_n, l2_a, l2_b, sync_seg, serpentine);
 }

@@ -195,6 +195,10 @@ void gemm_raster_override(int group_m, int group_n, int l2_a, int l2_b, int sync
   g_raster_override[2] = l2_a;
   g_raster_override[3] = l2_b;
 }
+// the kernel's tile walk, callable on the host (CPU test: every (row-tile, column-tile) exactly once for any knobs)
+void gemm_tile_coords_host(int t, int num_m, int num_n, int group_m, int group_n, int serpentine, int* mb, int* nb) {
+  gemm_tile_coords(t, num_m, num_n, group_m, group_n | (serpentine ? kRasterSerpentine : 0), *mb, *nb);
+}
 static unsigned long long l2_code(int c) { return c == 2 ? kL2EvictLast : c == 1 ? kL2EvictFirst : kL2EvictNormal; }
 static void gemm_raster_choice(int M, int N, int K, int eb, int bn, int cg, int num_sms, int& group, int& group_n,
                                unsigned long long& l2_a, unsigned long long& l2_b, int& sync_seg) {

@@ -138,20 +138,20 @@ struct GemmCfg {
 // from L2.  Which operand stays resident across waves is the launcher's choice: a wide G keeps the activation slab
 // [G * tile rows, K] while W streams; a narrow G with NC column-tiles keeps the W slab [NC * BN, K] while the
 // activations stream (once per super-group).
-__device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int NC, int& mb, int& nb) {
+__host__ __device__ __forceinline__ void gemm_tile_coords(int t, int num_m, int num_n, int G, int NC, int& mb, int& nb) {
   const bool serp = (NC >> 30) & 1;
   NC &= ~(1 << 30);
   int first_n = 0, ncs = num_n;
   if (NC > 0 && NC < num_n) {
     const int sg = t / (num_m * NC);
     first_n = sg * NC;
-    ncs = min(NC, num_n - first_n);
+    ncs = NC < num_n - first_n ? NC : num_n - first_n;
     t -= sg * num_m * NC;
   }
   const int per_group = G * ncs;
   const int g = t / per_group;
   const int first_m = g * G;
-  const int gsz = min(G, num_m - first_m);
+  const int gsz = G < num_m - first_m ? G : num_m - first_m;
   const int in_g = t - g * per_group;
   mb = first_m + in_g % gsz;
   const int c = in_g / gsz;

@@ -21,6 +21,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, int 
                 const GemmEpi& epi, int bn, int cg, int num_sms, cudaStream_t stream, SplitKWs ws = SplitKWs{nullptr, 0});
 bool splitk_eligible(int M, int N, int kind);
 void gemm_raster_override(int group_m, int group_n, int l2_a, int l2_b, int sync_seg, int serpentine);
+void gemm_tile_coords_host(int t, int num_m, int num_n, int group_m, int group_n, int serpentine, int* mb, int* nb);
 int gemm_grouped_launch(const void* A, long long lda, long long a_gs, const void* W, long long ldw, long long w_gs,
                         int groups, int M, int N, int K, int kind, float* out, long long ldo, long long out_gs,
                         const float* bias_f32, long long bias_gs, int bn, int cg, int num_sms, cudaStream_t stream);

@@ -53,6 +53,40 @@ def test_every_entry_point_has_header_derived_argtypes(lib):
     assert protos["ovla_bind_weight"][1][1] is C.c_char_p
 
 
+def test_gemm_tile_walk_visits_every_tile_once(lib):
+    """The persistent GEMM's rasterisation (gemm.cuh `gemm_tile_coords`: row groups inside column super-groups,
+    optionally serpentine) evaluated on the HOST through ovla_debug_gemm_tile_order: for every knob combination the
+    walk must be a bijection onto the num_m x num_n tiles -- a tile visited twice or never would be a silent wrong
+    result -- and must keep the locality it is there for: consecutive tiles of a group stay inside the group's rows and
+    the super-group's columns, and a serpentine walk enters each row group at the column the previous one left."""
+    def walk(num_m, num_n, G, NC, serp):
+        mb = (ctypes.c_int * (num_m * num_n))()
+        nb = (ctypes.c_int * (num_m * num_n))()
+        assert lib.ovla_debug_gemm_tile_order(num_m, num_n, G, NC, serp, mb, nb) == 0
+        return list(zip(mb, nb))
+
+    for num_m, num_n in [(1, 1), (1, 7), (9, 1), (3, 5), (16, 16), (17, 5), (36, 11), (283, 16), (72, 86)]:
+        for G in (1, 2, 3, 8, 16, 500):
+            for NC in (0, 1, 3, 8, 1000):
+                for serp in (0, 1):
+                    tiles = walk(num_m, num_n, G, NC, serp)
+                    assert sorted(tiles) == [(m, n) for m in range(num_m) for n in range(num_n)], (num_m, num_n, G, NC, serp)
+                    ncs = NC if 0 < NC < num_n else num_n
+                    per_sg = num_m * ncs
+                    for t, (m, n) in enumerate(tiles):
+                        sg, r = divmod(t, per_sg)
+                        assert sg * ncs <= n < min(num_n, (sg + 1) * ncs)          # inside its column super-group
+                        width = min(ncs, num_n - sg * ncs)
+                        assert m // G == r // (G * width)                          # inside its row group
+    # the default walks of the four Llama prefill GEMMs at bs = 256 (283 x {48, 16, 86, 16} tiles)
+    t = walk(283, 86, 16, 0, 1)
+    assert t[:3] == [(0, 0), (1, 0), (2, 0)] and t[16] == (0, 1)
+    assert t[16 * 86 - 1] == (15, 85) and t[16 * 86] == (16, 85) and t[2 * 16 * 86] == (32, 0)    # serpentine turn-around
+    t = walk(283, 16, 2, 8, 0)
+    assert t[:4] == [(0, 0), (1, 0), (0, 1), (1, 1)] and t[16] == (2, 0) and t[283 * 8] == (0, 8)
+    assert lib.ovla_debug_gemm_tile_order(0, 4, 1, 0, 0, None, None) != 0
+
+
 def test_library_contains_blackwell_instructions():
     """The shipped binary is sm_100a SASS with tcgen05 / TMA / TMEM instructions (no PTX-JIT, no fallback arch)."""
     import shutil
