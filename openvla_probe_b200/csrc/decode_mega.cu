@@ -103,6 +103,11 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 1) decode_step_kernel(const 
   __shared__ float s_sq[128];
   __shared__ float s_red[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (Measured and dropped, round 2: warp-major numbering of the global warps, which spreads the warps that own one output
+  // column more than the others -- N = 4096 on 1184 warps: 544 warps with 4 columns, 640 with 3 -- evenly over the CTAs
+  // instead of giving them all to CTAs 0-67.  The step did not move (2849 vs 2842 us): a phase lasts as long as ONE warp
+  // needs for its 4 columns at its latency-bound pace, whatever its neighbours on the SM do; evening that out needs a
+  // split along K, i.e. another summation order.)
   const int warp_g = blockIdx.x * kWarps + warp;
   const int n_warps = gridDim.x * kWarps;
   const int D = a.D, I = a.I, S = a.S;
