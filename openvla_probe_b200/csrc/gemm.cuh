@@ -17,6 +17,9 @@
 // [residual add -> round];  SwiGLU: silu(round(g)) -> round -> * round(u) -> round.
 #pragma once
 #include "ptx.cuh"
+#ifdef OVLA_DBG_EPI_TIMELINE
+#include <cstdio>
+#endif
 
 namespace ovla {
 
@@ -302,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const int slice = (t / tiles_mn) % shape.split_k;
+        const int slice = shape.split_k == 1 ? 0 : (t / tiles_mn) % shape.split_k;   // no divisions on the MMA issue path
         const int kb0 = slice * shape.kb_per_split, kb1 = min(num_k, kb0 + shape.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -333,17 +336,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t res_phase = 0;   // bit s: parity of this warp's residual-slot barrier s
     uint32_t n_out = 0, n_res = 0;   // chunks this warp has stored / residual chunks it has requested and consumed
     uint32_t n_req = 0;
-    for (int t = worker; t < num_tiles; t += num_workers) {
-      int mb, nb;
-      const int outer = t / tiles_mn;
-      const int slice = outer % shape.split_k, gidx = outer / shape.split_k;
-      gemm_tile_coords(t - outer * tiles_mn, num_m, num_n, shape.group_m, shape.group_n, mb, nb);
+#ifdef OVLA_DBG_EPI_TIMELINE   // debug variant only: where does an epilogue warp spend its cycles? (tools/gemm_epilogue_timeline.py)
+    long long tl[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long tl_t = clock64();
+    int tl_tiles = 0;
+#define OVLA_TL(i) { const long long now_ = clock64(); tl[i] += now_ - tl_t; tl_t = now_; }
+#else
+#define OVLA_TL(i)
+#endif
+    // Tile coordinates cost ~10 integer divisions (no hardware divider: ~2000 cycles), and with short K the epilogue
+    // warps ARE the critical path (profiles/r03a_epilogue_timeline.md): every 32 iterations lane l works out the
+    // coordinates of this worker's iteration i + l -- all lanes at once -- and each iteration fetches its own by shuffle.
+    int l_mb = 0, l_nb = 0, l_slice = 0, l_gidx = 0, iter = 0;
+    for (int t = worker; t < num_tiles; t += num_workers, ++iter) {
+      if ((iter & 31) == 0) {
+        const long long tl = static_cast<long long>(t) + static_cast<long long>(lane) * num_workers;
+        if (tl < num_tiles) {
+          const int outer = static_cast<int>(tl) / tiles_mn;
+          l_slice = outer % shape.split_k;
+          l_gidx = outer / shape.split_k;
+          gemm_tile_coords(static_cast<int>(tl) - outer * tiles_mn, num_m, num_n, shape.group_m, shape.group_n, l_mb, l_nb);
+        }
+      }
+      const int mb = __shfl_sync(0xffffffffu, l_mb, iter & 31), nb = __shfl_sync(0xffffffffu, l_nb, iter & 31);
+      const int slice = __shfl_sync(0xffffffffu, l_slice, iter & 31), gidx = __shfl_sync(0xffffffffu, l_gidx, iter & 31);
       const int row = mb * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
       const bool row_ok = row < shape.M;
       float rstd = 1.f;
       if constexpr (MODE == kModeSwiGLU || MODE == kModeQkvRope) rstd = fused_norm_rstd(epi, row, row_ok);
+      OVLA_TL(6)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      OVLA_TL(0)
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const int col0 = nb * BN;
 
@@ -366,7 +390,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (has_res && c < BN / 32 && col0 + c * 32 < shape.N) {
             if (lane == 0) {
               uint64_t* bar = &res_bar[(n_req % SL) * kEpiWarps + ew];
+#ifdef OVLA_GEMM_RELEASE_ARRIVE
               mbar_expect_tx(bar, Cfg::kEpiStageBytes);
+#else
+              mbar_expect_tx_relaxed(bar, Cfg::kEpiStageBytes);
+#endif
               tma_load_2d(&tmap_res, bar, res_slot(n_req), col0 + c * 32, row0);
             }
             ++n_req;
@@ -387,7 +415,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #endif
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
+          // the chunk's bias (all four 8-column pieces) and the first LayerScale piece are requested before the wait for
+          // the accumulator: inside the 8-column loop each of these loads sat behind a branch, with its full latency
+          // exposed (4 x ~250 cycles per chunk; the epilogue warps of a short-K GEMM are the critical path)
+          uint4 bq[4] = {};
+          uint4 sc_next = {};
+          if (epi.bias) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col + g * 8 < shape.N) bq[g] = *reinterpret_cast<const uint4*>(epi.bias + col + g * 8);
+          }
+          if (epi.scale) sc_next = *reinterpret_cast<const uint4*>(epi.scale + col);
           tmem_ld_wait();
+          OVLA_TL(1)
           float cs = 0.f;
           uint4 rr[4] = {};
           if (has_res) {
@@ -404,6 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();          // every lane has read its row: the slot may be refilled
             fetch_res(c + 2 * SL);
           }
+          OVLA_TL(2)
           // Rounding points of the reference's bf16 ops: linear (+ bias) -> [GELU] -> [LayerScale] -> [residual].  After
           // the first rounding the values travel as packed bf16 pairs: LayerScale and the residual add are single
           // bf16x2 instructions (bit-identical to fp32 arithmetic + rounding, see mul_bf16x2 / add_bf16x2) -- the
@@ -416,10 +457,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
             uint32_t pk[4];
+            const uint4 ss = sc_next;
+            if (epi.scale && g < 3 && cg + 8 < shape.N) sc_next = *reinterpret_cast<const uint4*>(epi.scale + cg + 8);
             if (cg < shape.N) {
               if (epi.bias) {
-                const uint4 bb = *reinterpret_cast<const uint4*>(epi.bias + cg);
-                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+                const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 f = unpack_bf16(bw[i]);
@@ -438,7 +480,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
               }
               if (epi.scale) {
-                const uint4 ss = *reinterpret_cast<const uint4*>(epi.scale + cg);
                 pk[0] = mul_bf16x2(pk[0], ss.x);
                 pk[1] = mul_bf16x2(pk[1], ss.y);
                 pk[2] = mul_bf16x2(pk[2], ss.z);
@@ -466,8 +507,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (c & 4) ss1 += cs; else ss0 += cs;
           uint8_t* so = out_slot(n_out);
+#ifdef OVLA_DBG_EPI_TIMELINE
+          asm volatile("" :: "r"(o4[0].x), "r"(o4[1].y), "r"(o4[2].z), "r"(o4[3].w) : "memory");   // the math is done here
+#endif
+          OVLA_TL(3)
           if (lane == 0) tma_store_wait_read<SL - 1>();   // the store that last used this slot has finished reading it
           __syncwarp();
+          OVLA_TL(4)
 #pragma unroll
           for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(so + lane * 64 + ((g ^ sw) << 4)) = o4[g];
 #ifndef OVLA_DBG_NO_STORE_FENCE   // timing experiments only
@@ -479,6 +525,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_commit();
           }
           ++n_out;
+          OVLA_TL(5)
         }
         if (epi.ss_out && row_ok && col0 < shape.N) {
           float* sp = epi.ss_out + static_cast<long long>(row) * epi.ss_ld + (col0 >> 7) * 2 + part;
@@ -768,10 +815,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+#ifdef OVLA_GEMM_RELEASE_ARRIVE   // A/B: the round-2a form (generic release in front of the arrive: MEMBAR + ERRBAR per tile)
         if constexpr (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0);
+#else
+        if constexpr (CG == 1) mbar_arrive_relaxed(&tmem_empty[acc]); else mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);
+#endif
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef OVLA_DBG_EPI_TIMELINE
+      ++tl_tiles;
+#endif
     }
+#ifdef OVLA_DBG_EPI_TIMELINE
+    if (MODE == kModeBf16 && lane == 0 && (warp == 4 || warp == 11) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tl_tiles > 1)
+      printf("EPI_TL cta %d warp %d tiles %d cycles/tile: acc_wait %lld tmem_ld %lld resid %lld math %lld slot_wait %lld store %lld release %lld\n",
+             blockIdx.x, warp, tl_tiles, tl[0] / tl_tiles, tl[1] / tl_tiles, tl[2] / tl_tiles, tl[3] / tl_tiles, tl[4] / tl_tiles,
+             tl[5] / tl_tiles, tl[6] / tl_tiles);
+#endif
   }
 
   // ------------------------------------------------------------ teardown
