@@ -228,7 +228,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       // wave alignment: segment g of the launch (tile iteration x segments per tile) starts once every CTA has issued
-      // the loads of segment g - 1; a CTA that runs out of tiles hands in its remaining arrivals at once
+      // the loads of segment g - 1; a CTA that runs out of tiles hands in its remaining arrivals at once.
+      // (Measured and dropped, profiles/r03e_producer_ab.md: sending the arrival 4 K blocks early to hide the counter
+      // round trip, and taking this thread's ~10 integer divisions per tile off the tile boundary -- into the middle
+      // of the tile, or out of the loop with the lane-parallel scheme of the epilogue warps -- all LOST 4-6 % on the
+      // Llama shapes: the divisions run in the shadow of the barrier round trip, and anything that lets the CTAs of a
+      // wave start a tile less exactly together costs L2 hits.)
       unsigned int* const sync = shape.sync;
       const int segs_per_tile = sync ? (num_k + shape.sync_seg - 1) / shape.sync_seg : 0;
       unsigned int seg_done = 0;
