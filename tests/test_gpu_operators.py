@@ -358,6 +358,44 @@ def test_gemm_rasterisation_and_wave_alignment_do_not_change_results(L, M, N, K,
         lib.ovla_debug_gemm_raster(-1, -1, -1, -1, -1, -1)
 
 
+def test_wave_aligned_gemms_on_two_streams_finish_and_agree(L):
+    """Two wave-aligned GEMMs launched at the same time on two streams each want every SM (1 CTA per SM): the second
+    grid becomes resident piecemeal while the first one drains, so its early CTAs sit at the first alignment point
+    until the rest arrives.  Each stream has its own counter words and a waiting producer gives up after ~4 M cycles,
+    so nothing can dead-lock; the results must equal the serial ones bit for bit and the whole thing must take
+    milliseconds, not time-outs."""
+    import time
+    _lib, lib = L
+    M, N, K = 8192 + 256, 4096, 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = [bf(torch.randn(M, K, generator=g, device="cuda") * 0.5) for _ in range(2)]
+    W = [bf(torch.randn(N, K, generator=g, device="cuda") * 0.03) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+    def call(i, out, st):
+        epi = _lib.GemmEpilogue()
+        _lib.check(lib.ovla_gemm(P(A[i]), K, P(W[i]), K, M, N, K, 0, 0, P(out), N, C.byref(epi), 0, 0,
+                                 C.c_void_p(st.cuda_stream) if st is not None else None))
+
+    ref = [torch.empty(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    for i in range(2):
+        call(i, ref[i], None)
+    torch.cuda.synchronize()
+    out = [torch.empty_like(r) for r in ref]
+    for i in range(2):
+        call(i, out[i], streams[i])       # first use of a stream allocates its counter words
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for rep in range(6):
+        for i in range(2):
+            call(i, out[i], streams[i])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    for i in range(2):
+        assert torch.equal(out[i], ref[i]), i
+    assert dt < 0.25, f"12 GEMMs of 0.28 TFLOP (~3 ms of work) took {dt:.3f} s: alignment waits are timing out"
+
+
 @pytest.mark.parametrize("B,ctx", [(1, 1), (2, 37), (3, 290), (5, 64)])
 def test_decode_rope_attention_and_cache_append(L, B, ctx):
     """Fused RoPE + KV append + 1-query attention == oracle llama attention step with a KV cache."""
