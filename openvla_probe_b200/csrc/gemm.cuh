@@ -420,17 +420,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #endif
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
-          // the chunk's bias (all four 8-column pieces) and the first LayerScale piece are requested before the wait for
+          // the chunk's bias and LayerScale (four 8-column pieces each) are requested before the wait for
           // the accumulator: inside the 8-column loop each of these loads sat behind a branch, with its full latency
           // exposed (4 x ~250 cycles per chunk; the epilogue warps of a short-K GEMM are the critical path)
-          uint4 bq[4] = {};
-          uint4 sc_next = {};
+          uint4 bq[4] = {}, sq[4] = {};
           if (epi.bias) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               if (col + g * 8 < shape.N) bq[g] = *reinterpret_cast<const uint4*>(epi.bias + col + g * 8);
           }
-          if (epi.scale) sc_next = *reinterpret_cast<const uint4*>(epi.scale + col);
+          if (epi.scale) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col + g * 8 < shape.N) sq[g] = *reinterpret_cast<const uint4*>(epi.scale + col + g * 8);
+          }
           tmem_ld_wait();
           OVLA_TL(1)
           float cs = 0.f;
@@ -454,62 +457,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // the first rounding the values travel as packed bf16 pairs: LayerScale and the residual add are single
           // bf16x2 instructions (bit-identical to fp32 arithmetic + rounding, see mul_bf16x2 / add_bf16x2) -- the
           // epilogue of a short-K GEMM is bound by its instruction count (profiles/r02q_gemm_epilogue_cost.md).
-          uint4 o4[4];
+          // The four phases run over the whole 32-column chunk one after the other (one run-time branch per phase, not
+          // per 8 columns): the erf-GELU of 16 independent pairs then schedules as one straight-line block
+          // (profiles/r03a_epilogue_timeline.md: fc1 spent 8500 of its 13000 epilogue cycles per tile here).
+          uint32_t pk[16];
+          if (epi.bias) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = col + g * 8;
-            float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-            uint32_t pk[4];
-            const uint4 ss = sc_next;
-            if (epi.scale && g < 3 && cg + 8 < shape.N) sc_next = *reinterpret_cast<const uint4*>(epi.scale + cg + 8);
-            if (cg < shape.N) {
-              if (epi.bias) {
-                const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(bw[i]);
-                  x[2 * i] += f.x;
-                  x[2 * i + 1] += f.y;
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
-              if (epi.gelu) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 f = unpack_bf16(pk[i]);
-                  gelu_erf_x2(f.x, f.y);
-                  pk[i] = pack_bf16(f.x, f.y);
-                }
-              }
-              if (epi.scale) {
-                pk[0] = mul_bf16x2(pk[0], ss.x);
-                pk[1] = mul_bf16x2(pk[1], ss.y);
-                pk[2] = mul_bf16x2(pk[2], ss.z);
-                pk[3] = mul_bf16x2(pk[3], ss.w);
-              }
-              if (has_res) {
-                pk[0] = add_bf16x2(pk[0], rr[g].x);
-                pk[1] = add_bf16x2(pk[1], rr[g].y);
-                pk[2] = add_bf16x2(pk[2], rr[g].z);
-                pk[3] = add_bf16x2(pk[3], rr[g].w);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
-            }
-            o4[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (epi.ss_out) {   // squares of the values as stored (bf16), in column order
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};   // zeros beyond N (those columns are clipped)
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 r = unpack_bf16(pk[i]);
-                cs = fmaf(r.x, r.x, cs);
-                cs = fmaf(r.y, r.y, cs);
+                const float2 f = unpack_bf16(bw[i]);
+                v[g * 8 + 2 * i] = __float_as_uint(__uint_as_float(v[g * 8 + 2 * i]) + f.x);
+                v[g * 8 + 2 * i + 1] = __float_as_uint(__uint_as_float(v[g * 8 + 2 * i + 1]) + f.y);
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          if (epi.gelu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float2 f = unpack_bf16(pk[j]);
+              gelu_erf_x2(f.x, f.y);
+              pk[j] = pack_bf16(f.x, f.y);
+            }
+          }
+          if (epi.scale) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              pk[4 * g] = mul_bf16x2(pk[4 * g], sq[g].x);
+              pk[4 * g + 1] = mul_bf16x2(pk[4 * g + 1], sq[g].y);
+              pk[4 * g + 2] = mul_bf16x2(pk[4 * g + 2], sq[g].z);
+              pk[4 * g + 3] = mul_bf16x2(pk[4 * g + 3], sq[g].w);
+            }
+          }
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              pk[4 * g] = add_bf16x2(pk[4 * g], rr[g].x);
+              pk[4 * g + 1] = add_bf16x2(pk[4 * g + 1], rr[g].y);
+              pk[4 * g + 2] = add_bf16x2(pk[4 * g + 2], rr[g].z);
+              pk[4 * g + 3] = add_bf16x2(pk[4 * g + 3], rr[g].w);
+            }
+          }
+          if (epi.ss_out) {   // squares of the values as stored (bf16), in column order
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 r = unpack_bf16(pk[j]);
+              cs = fmaf(r.x, r.x, cs);
+              cs = fmaf(r.y, r.y, cs);
+            }
+          }
+          uint4 o4[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           if (c & 4) ss1 += cs; else ss0 += cs;
           uint8_t* so = out_slot(n_out);
 #ifdef OVLA_DBG_EPI_TIMELINE
