@@ -183,6 +183,7 @@ extern "C" int ovla_create(const OvlaDims* dims, int device, OvlaEngine** out) {
   if (const char* fn = getenv("OVLA_FUSE_NORM")) e->fuse_norm = fn[0] != '0';
   if (const char* fr = getenv("OVLA_FUSE_NORM_MIN_ROWS")) e->fuse_norm_min_rows = std::max(1, atoi(fr));
   if (const char* dm = getenv("OVLA_DECODE_MEGA")) e->decode_mega = dm[0] != '0';
+  if (const char* gm = getenv("OVLA_GRAPH_MAX_BATCH")) e->graph_max_batch = std::max(0, atoi(gm));   // A/B knob
   if (const char* gr = getenv("OVLA_GRAPHS")) { if (gr[0] == '0') e->graph_max_batch = 0; }  // eager launches (for ncu)
   e->device = device;
   const OvlaDims& d = e->d;
