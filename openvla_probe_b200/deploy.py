@@ -2,9 +2,10 @@
 (`OpenVLAServer`: POST /act with {"image": ndarray, "instruction": str, "unnorm_key": optional} -> action).
 
 The reference handles one request at a time on one GPU (deploy.py:120-123).  Here concurrent requests are
-micro-batched: a worker thread drains the queue for at most `max_wait_ms` (or until `max_batch` requests of equal
-prompt length are waiting) and serves them with ONE fused batched `predict_action` pass -- the natural consumer of the
-batch-B capability of the engine.  Each request still receives exactly the B = 1 result (batch invariance).
+micro-batched: a worker thread drains the queue for at most `max_wait_ms` (or until `max_batch` requests are waiting)
+and serves them with ONE fused, ragged `predict_action` pass per un-normalisation key -- the natural consumer of the
+batch-B capability of the engine.  Each request still receives exactly the B = 1 result (batch / ragged invariance).
+`run()` is the reference's FastAPI + uvicorn shell (POST /act); `make_app()` returns the app without starting it.
 """
 from __future__ import annotations
 
@@ -35,10 +36,13 @@ def get_openvla_prompt(instruction: str, openvla_path: str) -> str:
 
 class OpenVLAServer:
     def __init__(self, vla, tokenizer: Callable[[str], Sequence[int]], openvla_path: str = "openvla/openvla-7b",
-                 max_batch: int = 16, max_wait_ms: float = 3.0) -> None:
-        """`vla`: an `OpenVLAForActionPrediction` (its engine must be created with max_batch >= `max_batch`);
-        `tokenizer(prompt) -> ids` (first id = BOS).  Frames must already have the model resolution (uint8 HxWx3)."""
+                 max_batch: int = 16, max_wait_ms: float = 3.0, pad_token_id: int = 0) -> None:
+        """`vla`: an `OpenVLAForActionPrediction` (its engine must be created with max_batch >= `max_batch` and a
+        max_prompt_len that covers the longest instruction); `tokenizer(prompt) -> ids` (first id = BOS);
+        `pad_token_id` fills the masked tail of shorter prompts (never attended).  Frames must already have the model
+        resolution (uint8 HxWx3)."""
         self.vla, self.tokenizer, self.openvla_path = vla, tokenizer, openvla_path
+        self.pad_token_id = pad_token_id
         self.max_batch, self.max_wait = max_batch, max_wait_ms / 1e3
         self._q: "queue.Queue" = queue.Queue()
         self._stop = threading.Event()
@@ -63,16 +67,24 @@ class OpenVLAServer:
                     batch.append(self._q.get(timeout=left))
                 except queue.Empty:
                     break
-            # one fused pass per (prompt length, unnorm_key) group: the engine takes full-length prompts only
+            # one fused pass per unnorm_key: instructions of different lengths go into ONE ragged batch, right-padded
+            # with an attention mask of ones then zeros (the tokenizer's padding_side="right"; causal attention never
+            # looks at the pads, so every request still gets its B = 1 answer -- DESIGN.md "Ragged batches")
             groups: Dict[Any, list] = {}
             for item in batch:
-                groups.setdefault((len(item["ids"]), item["unnorm_key"]), []).append(item)
-            for (_, key), items in groups.items():
+                groups.setdefault(item["unnorm_key"], []).append(item)
+            for key, items in groups.items():
                 try:
-                    ids = torch.tensor([it["ids"] for it in items], dtype=torch.int64)
+                    longest = max(len(it["ids"]) for it in items)
+                    ids = torch.full((len(items), longest), self.pad_token_id, dtype=torch.int64)
+                    mask = torch.zeros((len(items), longest), dtype=torch.int64)
+                    for r, it in enumerate(items):
+                        ids[r, :len(it["ids"])] = torch.tensor(it["ids"], dtype=torch.int64)
+                        mask[r, :len(it["ids"])] = 1
                     frames = torch.from_numpy(np.stack([it["image"] for it in items]))
                     px = self.vla.preprocess_frames(frames)
-                    actions = self.vla.predict_action(ids, unnorm_key=key, pixel_values=px, do_sample=False)
+                    actions = self.vla.predict_action(ids, unnorm_key=key, pixel_values=px, attention_mask=mask,
+                                                      do_sample=False)
                     actions = np.asarray(actions).reshape(len(items), -1)
                     self.batches_served.append(len(items))
                     for it, a in zip(items, actions):
@@ -103,13 +115,18 @@ class OpenVLAServer:
             logging.error(traceback.format_exc())
             return "error"
 
-    def run(self, host: str = "0.0.0.0", port: int = 8000) -> None:
-        import uvicorn
+    def make_app(self):
+        """The reference's FastAPI shell (deploy.py:120-123): POST /act -> predict_action(payload)."""
         from fastapi import FastAPI
 
         self.app = FastAPI()
         self.app.post("/act")(self.predict_action)
-        uvicorn.run(self.app, host=host, port=port)
+        return self.app
+
+    def run(self, host: str = "0.0.0.0", port: int = 8000) -> None:
+        import uvicorn
+
+        uvicorn.run(self.make_app(), host=host, port=port)
 
     def close(self) -> None:
         self._stop.set()
