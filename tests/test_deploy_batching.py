@@ -88,9 +88,13 @@ def test_fastapi_shell_serves_act_over_http():
     uvicorn = pytest.importorskip("uvicorn")
     pytest.importorskip("fastapi")
     srv = OpenVLAServer(_FakeVLA(), hash_tokenizer, max_batch=4, max_wait_ms=1.0)
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+    try:
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+    except OSError as ex:                      # a sandbox without loopback sockets: nothing to test here
+        srv.close()
+        pytest.skip(f"cannot bind a loopback port: {ex}")
     server = uvicorn.Server(uvicorn.Config(srv.make_app(), host="127.0.0.1", port=port, log_level="error"))
     th = threading.Thread(target=server.run, daemon=True)
     th.start()
